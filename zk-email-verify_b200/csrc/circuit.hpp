@@ -1,0 +1,172 @@
+// Circuit front-end: an R1CS + witness-program builder.
+//
+// The reference compiles `email-verifier.circom` with the circom compiler (un-vendored; CI pins v2.1.8 at
+// /root/reference/.github/workflows/action.yml:29-33) into an .r1cs and a WASM witness calculator.  circom
+// is not part of the reference tree, so this builder plays its role: templates (gadgets.cpp) call the
+// builder the way circom templates declare signals and constraints, and the builder emits
+//   * the R1CS (A, B, C as CSR over an interned coefficient table), and
+//   * a levelised witness program: one op per signal, ops grouped by dependency depth so that a
+//     device can evaluate a level in parallel and synchronise between levels.
+//
+// Semantics follow circom at optimisation level --O1 (the level the reference's docs recommend,
+// /root/reference/docs/zk-email-docs/UsageGuide/README.md:60-66): every `<==` of a non-trivial
+// expression produces a signal and a constraint; only `signal = signal` / `signal = constant`
+// aliases are elided.  Linear constraints are stored as A = B = 0, C = expr (as circom does).
+#pragma once
+#include "ff_host.hpp"
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+namespace zke {
+
+typedef uint32_t Var;
+static const Var TEMP_BIT = 0x80000000u;  // builder-time tag of scratch slots (not part of the R1CS)
+
+// Sparse linear combination over witness variables; variable 0 is the constant one.
+struct LC {
+    std::vector<std::pair<Var, Fr>> t;  // sorted by var, unique, non-zero coefficients
+
+    LC() {}
+    LC(Var v) { t.emplace_back(v, Fr::one()); }
+    static LC var(Var v) { return LC(v); }
+    static LC constant(const Fr& c) { LC r; if (!c.is_zero()) r.t.emplace_back(0, c); return r; }
+    static LC constant_i(int64_t c) { return constant(Fr::from_i64(c)); }
+    static LC term(Var v, const Fr& c) { LC r; if (!c.is_zero()) r.t.emplace_back(v, c); return r; }
+
+    bool is_zero() const { return t.empty(); }
+    bool is_const() const { return t.empty() || (t.size() == 1 && t[0].first == 0); }
+    Fr const_value() const { return t.empty() ? Fr::zero() : t[0].second; }
+    bool is_single_var(Var* v) const {
+        if (t.size() == 1 && t[0].first != 0 && t[0].second == Fr::one()) { *v = t[0].first; return true; }
+        return false;
+    }
+    LC operator+(const LC& o) const;
+    LC operator-(const LC& o) const;
+    LC operator*(const Fr& k) const;
+    LC neg() const;
+    LC& operator+=(const LC& o) { *this = *this + o; return *this; }
+    LC& operator-=(const LC& o) { *this = *this - o; return *this; }
+    // in-place "+= k * v" for accumulations that append increasing variables (fast path), falls back to merge
+    void add_term(Var v, const Fr& k);
+};
+inline LC operator*(const Fr& k, const LC& a) { return a * k; }
+
+enum OpCode : uint32_t {
+    OP_LIN = 0,     // dst = lc[a]
+    OP_QUAD = 1,    // dst = lc[a] * lc[b] + lc[c]
+    OP_SHRAND = 2,  // dst = (val[a] >> b) & (2^c - 1)   (c == 0: no mask); a is a variable / scratch slot
+    OP_INVZ = 3,    // dst = val[a] == 0 ? 0 : 1 / val[a]
+    OP_FPMUL = 4,   // big-integer hint of FpMul: aux[a..] = {n, k, a_vars[k], b_vars[k], p_vars[k]};
+                    // dst..dst+k-1 = q limbs, dst+k..dst+2k-1 = r limbs where a*b = q*p + r, 0 <= r < p
+};
+struct WOp {
+    uint32_t code;
+    Var dst;
+    uint32_t a, b, c;
+};
+
+struct SignalGroup {
+    std::string name;
+    uint32_t first;  // first witness index
+    uint32_t count;
+    int kind;        // 0 output, 1 public input, 2 private input
+};
+
+// Finalised, flat circuit description (what a device / an exporter consumes).
+struct Circuit {
+    std::string name;
+    uint32_t n_vars = 0;       // witness length m (w[0] = 1)
+    uint32_t n_temps = 0;      // scratch slots appended after the witness during evaluation
+    uint32_t n_outputs = 0, n_pub_inputs = 0, n_prv_inputs = 0;
+    uint32_t n_public() const { return n_outputs + n_pub_inputs; }   // "nPublic" of snarkjs
+    uint32_t n_inputs() const { return n_pub_inputs + n_prv_inputs; }
+    uint32_t n_constraints = 0;
+    std::vector<SignalGroup> groups;
+
+    std::vector<U256> coefs;   // interned coefficients, standard form; [0] = 1, [1] = r - 1 (i.e. -1)
+
+    // R1CS rows in CSR form; entry = (var, coef index)
+    std::vector<uint32_t> a_ptr, b_ptr, c_ptr;
+    std::vector<uint32_t> a_var, a_coef, b_var, b_coef, c_var, c_coef;
+    std::vector<uint16_t> scope_of_constraint;
+    std::vector<std::string> scopes;
+
+    // witness program, ops sorted by level; level_ptr has n_levels + 1 entries
+    std::vector<WOp> ops;
+    std::vector<uint32_t> level_ptr;
+    std::vector<uint32_t> lc_ptr, lc_var, lc_coef;  // LC pool referenced by OP_LIN / OP_QUAD
+    std::vector<uint32_t> aux;
+
+    uint32_t n_levels() const { return level_ptr.empty() ? 0 : (uint32_t)level_ptr.size() - 1; }
+    const SignalGroup* find_group(const std::string& n) const;
+    uint32_t domain_log2() const;  // smallest k with 2^k >= n_constraints + n_public + 1
+};
+
+class Builder {
+   public:
+    explicit Builder(const std::string& name);
+
+    // --- signal declaration (must precede any intermediate signal, mirrors circom's witness order:
+    //     [1, outputs, public inputs, private inputs, intermediates]) ---
+    std::vector<Var> declare_outputs(const std::string& name, uint32_t n);
+    std::vector<Var> declare_inputs(const std::string& name, uint32_t n, bool is_public);
+
+    // --- constraints / signals ---
+    LC signal(const LC& e);                                   // `signal x <== e` for a linear e
+    LC mul(const LC& a, const LC& b);                         // `signal x <== a*b`
+    LC mul_add(const LC& a, const LC& b, const LC& c);        // `signal x <== a*b + c`
+    void enforce_mul(const LC& a, const LC& b, const LC& c);  // a*b === c
+    void enforce_eq(const LC& a, const LC& b);                // a === b (linear)
+    void assign_output(Var out, const LC& e);                 // `out <== e` for a pre-declared output
+
+    // --- hints (`<--` in circom): no constraint is added, the caller constrains the result ---
+    Var fresh() { return new_var(); }
+    Var source_of(const LC& e);                                // variable or scratch slot holding e
+    Var hint_shrand(Var src, uint32_t shift, uint32_t nbits);  // (src >> shift) & (2^nbits - 1)
+    Var hint_invz(Var src);
+    Var hint_lin(const LC& e);                                 // a signal assigned (not constrained) to e
+    Var hint_fpmul(uint32_t n, uint32_t k, const std::vector<Var>& a, const std::vector<Var>& b,
+                   const std::vector<Var>& p);                 // returns base of q[k] ++ r[k]
+
+    // scope tag recorded with every constraint (for "Assert Failed: <scope>" messages)
+    void push_scope(const std::string& s);
+    void pop_scope();
+
+    bool materialize_linear = true;  // circom --O1 behaviour; false ~ --O2 (linear signals substituted)
+
+    Circuit finalize();
+
+    uint32_t num_vars() const { return next_var_; }
+    uint32_t num_constraints() const { return (uint32_t)c_.scope_of_constraint.size(); }
+
+   private:
+    Var new_var();
+    Var new_temp();
+    uint32_t intern(const Fr& c);
+    uint32_t add_prog_lc(const LC& e);
+    void push_row(std::vector<uint32_t>& ptr, std::vector<uint32_t>& var, std::vector<uint32_t>& coef, const LC& e);
+    void add_constraint(const LC& a, const LC& b, const LC& c);
+    void add_op(uint32_t code, Var dst, uint32_t a, uint32_t b, uint32_t c);
+
+    Circuit c_;
+    uint32_t next_var_ = 1;
+    uint32_t next_temp_ = 0;
+    bool decl_closed_ = false;
+    struct U256Hash {
+        size_t operator()(const U256& x) const { return (size_t)(x.v[0] * 0x9E3779B97F4A7C15ull ^ x.v[1] * 31 ^ x.v[2] * 131 ^ x.v[3]); }
+    };
+    std::unordered_map<U256, uint32_t, U256Hash> coef_index_;
+    std::vector<uint16_t> scope_stack_;
+    std::map<std::string, uint16_t> scope_index_;
+};
+
+struct ScopeGuard {
+    Builder& b;
+    ScopeGuard(Builder& b_, const std::string& s) : b(b_) { b.push_scope(s); }
+    ~ScopeGuard() { b.pop_scope(); }
+};
+
+}  // namespace zke

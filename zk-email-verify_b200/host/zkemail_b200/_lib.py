@@ -1,0 +1,57 @@
+"""ctypes binding of the C ABI declared in include/zkemail_b200.h.
+
+The shared library is the product: it holds the circuit front-end, the CUDA kernels and the Groth16 engine.
+There is no Python or CPU fallback - if the library is missing this module raises at import time, and every
+compute entry point fails when no CUDA device is present.
+"""
+from __future__ import annotations
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get(
+    "ZKEMAIL_B200_LIB", os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libzkemail_b200.so"))
+)
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found - build it first (python -c 'import __graft_entry__ as g; g.build()' "
+        "or make -C zk-email-verify_b200/csrc); there is no fallback implementation"
+    )
+lib = ctypes.CDLL(LIB_PATH)
+
+c_void_p, c_char_p, c_size_t = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t
+c_u32, c_u64, c_i64, c_int = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int
+ERRCAP = 4096
+
+
+class CircuitInfo(ctypes.Structure):
+    _fields_ = [(n, c_u32) for n in (
+        "n_vars", "n_temps", "n_outputs", "n_pub_inputs", "n_prv_inputs", "n_public", "n_constraints",
+        "n_levels", "n_ops", "n_coefs", "domain_log2", "n_groups")] + [(n, c_u64) for n in ("nnz_a", "nnz_b", "nnz_c")]
+
+
+def _sig(name, restype, argtypes):
+    fn = getattr(lib, name)
+    fn.restype = restype
+    fn.argtypes = argtypes
+    return fn
+
+
+zke_circuit_build = _sig("zke_circuit_build", c_void_p, [c_char_p, ctypes.POINTER(c_i64), c_size_t, c_char_p, c_size_t])
+zke_circuit_free = _sig("zke_circuit_free", None, [c_void_p])
+zke_circuit_get_info = _sig("zke_circuit_get_info", c_int, [c_void_p, ctypes.POINTER(CircuitInfo)])
+zke_circuit_group = _sig("zke_circuit_group", c_int, [c_void_p, c_u32, c_char_p, c_size_t, ctypes.POINTER(c_u32),
+                                                       ctypes.POINTER(c_u32), ctypes.POINTER(c_int)])
+zke_circuit_input_offset = _sig("zke_circuit_input_offset", c_i64, [c_void_p, c_char_p, ctypes.POINTER(c_u32)])
+zke_circuit_array = _sig("zke_circuit_array", c_void_p, [c_void_p, c_int, ctypes.POINTER(c_size_t)])
+zke_circuit_scope_name = _sig("zke_circuit_scope_name", c_char_p, [c_void_p, c_u32])
+zke_device_count = _sig("zke_device_count", c_int, [])
+zke_version = _sig("zke_version", c_char_p, [])
+
+# array selectors (enum in the header)
+(ARR_COEFS, ARR_A_PTR, ARR_A_VAR, ARR_A_COEF, ARR_B_PTR, ARR_B_VAR, ARR_B_COEF, ARR_C_PTR, ARR_C_VAR, ARR_C_COEF,
+ ARR_OPS, ARR_LEVEL_PTR, ARR_LC_PTR, ARR_LC_VAR, ARR_LC_COEF, ARR_AUX, ARR_SCOPE_OF_CONSTRAINT) = range(17)
+
+
+class ZkeError(RuntimeError):
+    pass
