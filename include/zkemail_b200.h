@@ -83,6 +83,76 @@ enum {
 const void* zke_circuit_array(const zke_circuit* c, int which, size_t* n_elems);
 const char* zke_circuit_scope_name(const zke_circuit* c, uint32_t scope_index);
 
+
+/* ---------------------------------------------------------------------------------------------------
+ * Proving key.  zke_setup() is a TOY trusted setup (`snarkjs groth16 setup` role,
+ * /root/reference/docs/zk-email-docs/UsageGuide/README.md:139-153): tau, alpha, beta, gamma, delta are derived
+ * from `seed`, i.e. the toxic waste is known - benchmark / test keys only.  The field side runs on the host, the
+ * ~5m + N fixed-base scalar multiplications on GPU `device`; the key stays resident on that GPU.
+ * ------------------------------------------------------------------------------------------------- */
+zke_zkey* zke_setup(const zke_circuit* c, uint64_t seed, int device, char* err, size_t errcap);
+void zke_zkey_free(zke_zkey* z);
+int zke_zkey_info(const zke_zkey* z, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_log2);
+/* zkey sections (iden3 .zkey numbering where one exists: 3 IC, 5 A, 6 B1, 7 B2, 8 C/"L", 9 H; header points apart). */
+enum {
+    ZKE_SEC_ALPHA1 = 101, ZKE_SEC_BETA1 = 102, ZKE_SEC_DELTA1 = 103,
+    ZKE_SEC_BETA2 = 104, ZKE_SEC_GAMMA2 = 105, ZKE_SEC_DELTA2 = 106,
+    ZKE_SEC_IC = 3, ZKE_SEC_A = 5, ZKE_SEC_B1 = 6, ZKE_SEC_B2 = 7, ZKE_SEC_C = 8, ZKE_SEC_H = 9
+};
+/* Copies a section to host memory as affine points, standard-form LE coordinates (G1 64 bytes: x,y;
+ * G2 128 bytes: x.c0,x.c1,y.c0,y.c1; infinity = zeros).  Returns the number of points (with out == NULL: just the
+ * count), < 0 on error.  Sections A/B1/B2/C have n_vars entries (C is infinity for the public signals). */
+int64_t zke_zkey_section(const zke_zkey* z, int section, uint8_t* out, size_t cap);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Contexts: circuit (+ optional proving key) resident on one GPU with work buffers for `max_batch` emails.
+ * One host thread per context (or external locking).  All calls are synchronous at the ABI.
+ * ------------------------------------------------------------------------------------------------- */
+zke_ctx* zke_ctx_open(const zke_circuit* c, const zke_zkey* zkey_or_null, int device, uint32_t max_batch,
+                      char* err, size_t errcap);
+void zke_ctx_close(zke_ctx* x);
+void* zke_ctx_stream(const zke_ctx* x);      /* the cudaStream_t all of the context's work is enqueued on */
+uint64_t zke_kernel_launches(void);          /* kernels launched by this library since it was loaded */
+
+/* calculateWitness + checkConstraints for a batch (circom_tester verbs; witness step of fullProve).
+ * inputs: [batch][n_inputs][32] in witness order (see zke_circuit_input_offset).  wtns_out (optional):
+ * [batch][n_vars][32], the `.wtns` payload.  status (optional): per email, -1 = satisfied, else the index of
+ * the first violated constraint.  Returns the number of failing emails (message: "Assert Failed: ..."). */
+int zke_witness(zke_ctx* x, const uint8_t* inputs, size_t batch, uint8_t* wtns_out, int32_t* status,
+                char* err, size_t errcap);
+/* Makes host witnesses resident (snarkjs `groth16 prove zkey wtns` entry). */
+int zke_load_witness(zke_ctx* x, const uint8_t* wtns, size_t batch, char* err, size_t errcap);
+/* Groth16 prove for the resident witnesses (snarkjs.groth16.prove).  rs (optional): [batch][2][32] fixed blinding
+ * scalars r, s (parity tests); NULL draws them from /dev/urandom.  proofs_out: [batch][8][32] =
+ * A.x, A.y, B.x.c0, B.x.c1, B.y.c0, B.y.c1, C.x, C.y (standard form, LE).  publics_out: [batch][n_public][32]. */
+int zke_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs_out, uint8_t* publics_out,
+              int32_t* status, char* err, size_t errcap);
+/* witness + prove in one call with host buffers (snarkjs.groth16.fullProve,
+ * /root/reference/packages/helpers/src/chunked-zkey.ts:80-84). */
+int zke_fullprove(zke_ctx* x, const uint8_t* inputs, size_t batch, const uint8_t* rs, uint8_t* proofs_out,
+                  uint8_t* publics_out, int32_t* status, char* err, size_t errcap);
+
+/* ---------------------------------------------------------------------------------------------------
+ * JSON faces of the boundary (snarkjs file formats; shapes as in
+ * /root/reference/packages/rust-verifier/tests/data/proof_of_twitter/{vkey,proof,public}.json).
+ * String outputs: pass the buffer capacity in *len; on return *len = bytes needed incl. NUL (rc -2 if too small).
+ * ------------------------------------------------------------------------------------------------- */
+/* snarkjs.groth16.verify(vkey, publicSignals, proof): 1 valid, 0 invalid, < 0 malformed input.  Host only. */
+int zke_verify_json(const char* vkey_json, const char* public_json, const char* proof_json, char* err, size_t errcap);
+/* `snarkjs zkey export verificationkey` (vk_alphabeta_12 omitted: neither verifier needs it). */
+int zke_zkey_vkey_json(const zke_zkey* z, char* out, size_t* len);
+/* zke_prove output -> proof.json / public.json */
+int zke_proof_to_json(const uint8_t* proof256, const uint8_t* publics, uint32_t n_public, char* proof_json, size_t* proof_len,
+                      char* public_json, size_t* public_len);
+/* input.json ({signal: decimal string | number | nested arrays}) -> packed inputs in witness order */
+int zke_pack_inputs_json(const zke_circuit* c, const char* input_json, uint8_t* out, size_t cap, char* err, size_t errcap);
+/* snarkjs.groth16.fullProve(input, wasm, zkey) for one email: JSON in, proof.json + public.json out */
+int zke_fullprove_json(zke_ctx* x, const zke_circuit* c, const char* input_json, char* proof_json, size_t* proof_len,
+                       char* public_json, size_t* public_len, char* err, size_t errcap);
+/* Diagnostic: the FpMul big-integer hint evaluated on the host with the same code the witness kernel runs
+ * (a, b, p: k limbs of 32 bytes LE; q, r out likewise). */
+int zke_selftest_fpmul_hint(uint32_t n, uint32_t k, const uint8_t* a, const uint8_t* b, const uint8_t* p, uint8_t* q, uint8_t* r);
+
 /* Library / device introspection.  zke_device_count() returns 0 when no CUDA device is usable;
  * every compute entry point then fails with a negative code (no CPU fallback exists). */
 int zke_device_count(void);

@@ -1,0 +1,162 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`), all through the C ABI.
+
+  * witness kernel vs the CPU oracle (bit-exact, whole witness vector) on every template family and on the
+    reference's test circuit EmailVerifier(640, 768, 121, 17) with `public [pubkey]`;
+  * accept / reject behaviour ("Assert Failed") on tampered inputs;
+  * Groth16 proofs from the GPU prover verify under the oracle's pairing verifier (itself pinned on the reference's
+    proof_of_twitter fixture) and under the product's own host verifier.
+"""
+import hashlib
+import random
+import pytest
+
+import zkemail_b200 as z
+from zkutil import oracle_witness, AssertFailed as OracleAssertFailed
+from oracle import bn254
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(circuit, zkey=None, batch=1):
+    return z.Context(circuit, zkey, device=0, max_batch=batch)
+
+
+def _gpu_vs_oracle(circuit, inputs_list):
+    ctx = _ctx(circuit, batch=len(inputs_list))
+    packed = b"".join(circuit.pack_inputs(i) for i in inputs_list)
+    wt, status = ctx.witness(packed, len(inputs_list))
+    m = circuit.info.n_vars
+    assert status == [-1] * len(inputs_list)
+    for k, inp in enumerate(inputs_list):
+        ref = oracle_witness(circuit, inp)
+        assert wt[32 * m * k: 32 * m * (k + 1)] == ref.raw(), f"witness mismatch for batch element {k}"
+    ctx.close()
+
+
+def test_witness_multiplier():
+    _gpu_vs_oracle(z.Circuit("Multiplier"), [{"a": 3, "b": 5}, {"a": z.FR_MODULUS - 1, "b": 12345678901234567890}])
+
+
+def test_witness_fpmul():
+    rnd = random.Random(1)
+    n, k = 121, 17
+    cases = []
+    for _ in range(3):
+        p = rnd.getrandbits(2048) | (1 << 2047) | 1
+        a, b = rnd.randrange(p), rnd.randrange(p)
+        lim = lambda x: [(x >> (n * i)) & ((1 << n) - 1) for i in range(k)]
+        cases.append({"a": lim(a), "b": lim(b), "p": lim(p)})
+    _gpu_vs_oracle(z.Circuit("FpMul", [n, k]), cases)
+    _gpu_vs_oracle(z.Circuit("FpMul", [2, 4]), [{"a": [1, 0, 1, 0], "b": [0, 1, 1, 0], "p": [1, 1, 1, 1]}])
+
+
+def test_witness_base64_and_regex_reveal():
+    _gpu_vs_oracle(z.Circuit("Base64Lookup"), [{"in": c} for c in (65, 90, 97, 122, 48, 57, 43, 47, 61)])
+    arr = [0] * 34
+    arr[5:13] = list(b"zk email")
+    _gpu_vs_oracle(z.Circuit("SelectRegexReveal", [34, 8]), [{"in": arr, "startIndex": 5}])
+
+
+def test_witness_sha256():
+    c = z.Circuit("Sha256Bytes", [128])
+    cases = []
+    for msg in (b"", b"hello world", bytes(range(100))):
+        padded, plen = z.sha256_pad(msg, 128)
+        cases.append({"paddedIn": list(padded), "paddedInLength": plen})
+    _gpu_vs_oracle(c, cases)
+    # and the digest really is SHA-256 (sha.test.ts)
+    ctx = _ctx(c)
+    padded, plen = z.sha256_pad(b"hello world", 128)
+    wt, _ = ctx.witness(c.pack_inputs({"paddedIn": list(padded), "paddedInLength": plen}), 1)
+    first, count, _ = c.groups["out"]
+    bits = [int.from_bytes(wt[32 * (first + i): 32 * (first + i) + 32], "little") for i in range(count)]
+    digest = hashlib.sha256(b"hello world").digest()
+    assert bits == [(b >> (7 - j)) & 1 for b in digest for j in range(8)]
+
+
+def test_witness_rsa_and_reject():
+    c = z.Circuit("RSAVerifier65537", [121, 17])
+    from test_templates_sha_rsa import MESSAGE, SIG_1024, PUB_1024
+    good = {"signature": z.to_circom_bigint_bytes(SIG_1024), "modulus": z.to_circom_bigint_bytes(PUB_1024), "message": MESSAGE}
+    _gpu_vs_oracle(c, [good])
+    bad = dict(good)
+    bad["message"] = [str(int(MESSAGE[0]) + 1)] + MESSAGE[1:]
+    ctx = _ctx(c, batch=2)
+    with pytest.raises(z.AssertFailed, match="Assert Failed"):
+        ctx.witness(c.pack_inputs(good) + c.pack_inputs(bad), 2)
+    _, status = ctx.witness(c.pack_inputs(good) + c.pack_inputs(bad), 2, raise_on_fail=False)
+    assert status[0] == -1 and status[1] >= 0
+    with pytest.raises(OracleAssertFailed):
+        oracle_witness(c, bad)
+
+
+@pytest.fixture(scope="module")
+def email_setup():
+    c = z.Circuit("EmailVerifier", [640, 768, 121, 17, 0, 0, 0, 0, 1])
+    key = z.synthetic.generate_key()
+    inputs = []
+    for i in range(3):
+        email = z.synthetic.make_signed_email(i, key, body_len=512)
+        dk = z.verify_dkim_signature(email, resolver=lambda n, t: [z.synthetic.key_record(key)])
+        inputs.append(z.generate_email_verifier_inputs_from_dkim_result(dk, {"maxHeadersLength": 640, "maxBodyLength": 768}))
+    return c, inputs
+
+
+def test_witness_email_verifier_test_circuit(email_setup):
+    c, inputs = email_setup
+    _gpu_vs_oracle(c, inputs)
+
+
+def test_email_verifier_rejects_tampering(email_setup):
+    c, inputs = email_setup
+    ctx = _ctx(c, batch=3)
+    bad_sig = dict(inputs[0]); bad_sig["signature"] = [str(int(bad_sig["signature"][0]) ^ 1)] + list(bad_sig["signature"][1:])
+    bad_body = dict(inputs[1]); body = list(bad_body["emailBody"]); body[7] = str((int(body[7]) + 1) % 128); bad_body["emailBody"] = body
+    packed = c.pack_inputs(bad_sig) + c.pack_inputs(bad_body) + c.pack_inputs(inputs[2])
+    _, status = ctx.witness(packed, 3, want_witness=False, raise_on_fail=False)
+    assert status[0] >= 0 and status[1] >= 0 and status[2] == -1
+
+
+def _prove_and_verify(circuit, inputs_list, seed=7):
+    zk = z.Zkey(circuit, seed=seed, device=0)
+    vkey = zk.vkey()
+    ctx = _ctx(circuit, zk, batch=len(inputs_list))
+    packed = b"".join(circuit.pack_inputs(i) for i in inputs_list)
+    proofs, publics, status = ctx.fullprove(packed, len(inputs_list))
+    npub = circuit.info.n_public
+    out = []
+    for k in range(len(inputs_list)):
+        proof, pubs = z.proof_to_json(proofs[256 * k: 256 * (k + 1)], publics[32 * npub * k: 32 * npub * (k + 1)], npub)
+        assert z.verify(vkey, pubs, proof), "product verifier rejected the GPU proof"
+        assert bn254.groth16_verify(vkey, pubs, proof), "oracle verifier rejected the GPU proof"
+        bad = list(pubs)
+        if bad:
+            bad[0] = str((int(bad[0]) + 1) % z.FR_MODULUS)
+            assert not bn254.groth16_verify(vkey, bad, proof)
+        out.append((proof, pubs))
+    ctx.close()
+    return out
+
+
+def test_prove_multiplier():
+    res = _prove_and_verify(z.Circuit("Multiplier"), [{"a": 3, "b": 5}, {"a": 11, "b": 2}])
+    assert res[0][1] == [str(3 * 5 * 5 + 3), "3"]
+
+
+def test_prove_fpmul_and_poseidon():
+    _prove_and_verify(z.Circuit("FpMul", [2, 4]), [{"a": [1, 0, 1, 0], "b": [0, 1, 1, 0], "p": [1, 1, 1, 1]}])
+    _prove_and_verify(z.Circuit("Poseidon", [2]), [{"inputs": [1, 2]}])
+
+
+def test_prove_sha256():
+    c = z.Circuit("Sha256Bytes", [64])
+    padded, plen = z.sha256_pad(b"abc", 64)
+    res = _prove_and_verify(c, [{"paddedIn": list(padded), "paddedInLength": plen}])
+    digest = hashlib.sha256(b"abc").digest()
+    assert res[0][1] == [str((b >> (7 - j)) & 1) for b in digest for j in range(8)]
+
+
+def test_prove_email_verifier_test_circuit(email_setup):
+    c, inputs = email_setup
+    res = _prove_and_verify(c, inputs[:2])
+    assert res[0][1][3:] == [str(int(x)) for x in inputs[0]["pubkey"]]

@@ -2,6 +2,7 @@
 #include "../../include/zkemail_b200.h"
 #include "engine.hpp"
 #include "gadgets.hpp"
+#include "bigdiv.hpp"
 #include <cstdio>
 #include <cstring>
 
@@ -14,6 +15,16 @@ void set_err(char* err, size_t cap, const std::string& msg) {
     size_t n = msg.size() < cap - 1 ? msg.size() : cap - 1;
     memcpy(err, msg.data(), n);
     err[n] = 0;
+}
+void random_scalar(U256& out) {
+    FILE* f = fopen("/dev/urandom", "rb");
+    if (!f) throw std::runtime_error("cannot open /dev/urandom");
+    for (;;) {
+        if (fread(out.v, 1, 32, f) != 32) { fclose(f); throw std::runtime_error("short read from /dev/urandom"); }
+        out.v[3] &= 0x3FFFFFFFFFFFFFFFull;   // 254 bits, then rejection
+        if (u256_cmp(out, fr_params().p) < 0) break;
+    }
+    fclose(f);
 }
 }  // namespace zke
 
@@ -236,6 +247,11 @@ const void* zke_circuit_array(const zke_circuit* c, int which, size_t* n) {
 const char* zke_circuit_scope_name(const zke_circuit* c, uint32_t i) {
     if (!c || i >= c->c.scopes.size()) return nullptr;
     return c->c.scopes[i].c_str();
+}
+
+int zke_selftest_fpmul_hint(uint32_t n, uint32_t k, const uint8_t* a, const uint8_t* b, const uint8_t* p, uint8_t* q, uint8_t* r) {
+    if (k > 32) return 1;
+    return fpmul_hint_words(n, k, (const uint32_t*)a, (const uint32_t*)b, (const uint32_t*)p, (uint32_t*)q, (uint32_t*)r);
 }
 
 const char* zke_version(void) { return "zkemail_b200 0.1 (sm_100a)"; }

@@ -1,0 +1,548 @@
+// Engine: device-resident proving key + circuit, trusted setup on the GPU, batched witness + Groth16 prove.
+// This is the translation unit nvcc compiles (it includes the kernel files so that the __constant__ field
+// parameters exist once); everything CUDA-facing of the C ABI lives here.
+#include "ff.cuh"
+namespace zke { namespace dev { unsigned long long g_kernel_launches = 0; } }
+#include "witness.cu"
+#include "matvec.cu"
+#include "ntt.cu"
+#include "msm.cu"
+#include "fixed_base.cu"
+
+#include "../../include/zkemail_b200.h"
+#include "engine.hpp"
+#include "ec_host.hpp"
+#include "setup_host.hpp"
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <thread>
+
+using namespace zke;
+
+#define CUDA_OK(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr); } while (0)
+
+namespace {
+
+struct DevBuf {
+    uint8_t* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void alloc(size_t n) { release(); if (n) { CUDA_OK(cudaMalloc(&p, n)); bytes = n; } }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    template <class T> void upload(const std::vector<T>& v) {
+        alloc(v.size() * sizeof(T));
+        if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+};
+
+void fill_consts(dev::FieldConsts& c, const FieldParams& p) {
+    memcpy(c.mod, p.p.v, 32); memcpy(c.r, p.r.v, 32); memcpy(c.r2, p.r2.v, 32);
+    c.inv = (uint32_t)p.inv;
+}
+
+void select_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) throw std::runtime_error("no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= n) throw std::runtime_error("bad device index");
+    CUDA_OK(cudaSetDevice(device));
+    dev::FieldConsts fr, fq;
+    fill_consts(fr, fr_params());
+    fill_consts(fq, fq_params());
+    CUDA_OK(cudaMemcpyToSymbol(dev::FR_C, &fr, sizeof fr));
+    CUDA_OK(cudaMemcpyToSymbol(dev::FQ_C, &fq, sizeof fq));
+}
+
+// 32 x 256 window table of multiples of a generator, affine Montgomery, entry d = 0 is infinity
+template <class F>
+std::vector<AffineH<F>> window_table(const AffineH<F>& gen) {
+    std::vector<AffineH<F>> t(32 * 256, AffineH<F>::inf());
+    JacobianH<F> base = JacobianH<F>::from_affine(gen);
+    for (int w = 0; w < 32; ++w) {
+        JacobianH<F> acc = JacobianH<F>::inf();
+        for (int d = 1; d < 256; ++d) {
+            acc = acc.add(base);
+            t[w * 256 + d] = acc.to_affine();
+        }
+        for (int k = 0; k < 8; ++k) base = base.dbl();
+    }
+    return t;
+}
+
+std::vector<U256> to_standard(const std::vector<Fr>& v) {
+    std::vector<U256> out(v.size());
+    const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t)
+        th.emplace_back([&, t]() { for (size_t i = v.size() * t / T; i < v.size() * (t + 1) / T; ++i) out[i] = v[i].to_u256(); });
+    for (auto& x : th) x.join();
+    return out;
+}
+
+template <class F>
+void put_le(uint8_t* dst, const F& x);
+template <> void put_le<Fq>(uint8_t* dst, const Fq& x) { U256 s = x.to_u256(); memcpy(dst, s.v, 32); }
+
+}  // namespace
+
+struct zke_zkey {
+    uint32_t n_vars = 0, n_public = 0, log_n = 0;
+    int device = 0;
+    G1AffineH alpha1, beta1, delta1;
+    G2AffineH beta2, gamma2, delta2;
+    std::vector<G1AffineH> ic;
+    DevBuf A, B1, B2, C, H;   // affine Montgomery points on the device
+};
+
+struct zke_ctx {
+    const zke_circuit* circuit = nullptr;
+    const zke_zkey* zkey = nullptr;
+    int device = 0;
+    uint32_t max_batch = 0;
+    cudaStream_t stream = nullptr;
+    // circuit on device
+    DevBuf ops, level_ptr, lc_ptr, lc_terms, aux, coef_r, small_inv;
+    DevBuf a_ptr, a_terms, b_ptr, b_terms, c_ptr, c_terms;
+    dev::DevProgram prog;
+    dev::DevR1cs r1cs;
+    // ntt
+    DevBuf tw_fwd, tw_inv, coset_scale;
+    dev::NttTables ntt;
+    // work buffers
+    size_t stride = 0;           // witness elements per email (n_vars + n_temps)
+    DevBuf w_all, inputs, va, vb, vc, vd, msm_ws, results, first_bad;
+    uint32_t loaded = 0;         // number of witnesses currently resident
+    std::vector<uint32_t> bad_host;
+};
+
+// ------------------------------------------------------------------------------------------------ setup
+static zke_zkey* do_setup(const zke_circuit* zc, uint64_t seed, int device) {
+    select_device(device);
+    const Circuit& c = zc->c;
+    SetupScalars S = compute_setup_scalars(c, seed);
+    std::unique_ptr<zke_zkey> zk(new zke_zkey());
+    zk->n_vars = c.n_vars; zk->n_public = c.n_public(); zk->log_n = S.log_n; zk->device = device;
+    const size_t N = (size_t)1 << S.log_n;
+    const uint32_t m = c.n_vars, l = c.n_public();
+
+    G1JacH g1 = G1JacH::from_affine(g1_generator());
+    G2JacH g2 = G2JacH::from_affine(g2_generator());
+    zk->alpha1 = g1.mul(S.alpha.to_u256()).to_affine();
+    zk->beta1 = g1.mul(S.beta.to_u256()).to_affine();
+    zk->delta1 = g1.mul(S.delta.to_u256()).to_affine();
+    zk->beta2 = g2.mul(S.beta.to_u256()).to_affine();
+    zk->gamma2 = g2.mul(S.gamma.to_u256()).to_affine();
+    zk->delta2 = g2.mul(S.delta.to_u256()).to_affine();
+
+    DevBuf t1, t2, scal, scratch;
+    t1.upload(window_table<Fq>(g1_generator()));
+    t2.upload(window_table<Fq2>(g2_generator()));
+    const uint32_t SLAB = 1u << 20;
+    scratch.alloc((size_t)SLAB * sizeof(dev::G2XYZZ));
+    cudaStream_t st = nullptr;
+
+    auto run_g1 = [&](const std::vector<Fr>& s, DevBuf& out) {
+        std::vector<U256> std_s = to_standard(s);
+        scal.upload(std_s);
+        out.alloc(s.size() * sizeof(dev::G1Affine));
+        for (size_t off = 0; off < s.size(); off += SLAB) {
+            uint32_t cnt = (uint32_t)std::min<size_t>(SLAB, s.size() - off);
+            dev::fixed_base_batch<dev::Fq>(t1.p, scal.p + 32 * off, cnt, scratch.p, out.p + sizeof(dev::G1Affine) * off, st);
+        }
+        CUDA_OK(cudaStreamSynchronize(st));
+    };
+    run_g1(S.a, zk->A);
+    run_g1(S.b, zk->B1);
+    run_g1(S.kc, zk->C);
+    run_g1(S.h, zk->H);
+    {
+        std::vector<U256> std_s = to_standard(S.b);
+        scal.upload(std_s);
+        zk->B2.alloc((size_t)m * sizeof(dev::G2Affine));
+        for (size_t off = 0; off < m; off += SLAB) {
+            uint32_t cnt = (uint32_t)std::min<size_t>(SLAB, m - off);
+            dev::fixed_base_batch<dev::Fq2>(t2.p, scal.p + 32 * off, cnt, scratch.p, zk->B2.p + sizeof(dev::G2Affine) * off, st);
+        }
+        CUDA_OK(cudaStreamSynchronize(st));
+    }
+    // IC = first l+1 entries of the kc points; they are not part of the C ("L") section
+    zk->ic.resize(l + 1);
+    CUDA_OK(cudaMemcpy(zk->ic.data(), zk->C.p, sizeof(G1AffineH) * (l + 1), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemset(zk->C.p, 0, sizeof(G1AffineH) * (l + 1)));
+    (void)N;
+    return zk.release();
+}
+
+// ------------------------------------------------------------------------------------------------ ctx
+static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, uint32_t max_batch) {
+    select_device(device);
+    const Circuit& c = zc->c;
+    if (zk && (zk->n_vars != c.n_vars || zk->n_public != c.n_public() || zk->log_n != c.domain_log2()))
+        throw std::runtime_error("zkey does not belong to this circuit");
+    if (zk && zk->device != device) throw std::runtime_error("zkey lives on another device");
+    if (max_batch == 0) throw std::runtime_error("max_batch must be positive");
+    std::unique_ptr<zke_ctx> x(new zke_ctx());
+    x->circuit = zc; x->zkey = zk; x->device = device; x->max_batch = max_batch;
+    CUDA_OK(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
+
+    // witness program
+    {
+        std::vector<uint32_t> packed(4 * c.ops.size());
+        for (size_t i = 0; i < c.ops.size(); ++i) {
+            const WOp& o = c.ops[i];
+            if (o.c >= (1u << 28)) throw std::runtime_error("witness program too large for the packed op format");
+            packed[4 * i + 0] = o.dst; packed[4 * i + 1] = o.a; packed[4 * i + 2] = o.b; packed[4 * i + 3] = o.c | (o.code << 28);
+        }
+        x->ops.upload(packed);
+        x->level_ptr.upload(c.level_ptr);
+        x->lc_ptr.upload(c.lc_ptr);
+        std::vector<uint32_t> terms(2 * c.lc_var.size());
+        for (size_t i = 0; i < c.lc_var.size(); ++i) { terms[2 * i] = c.lc_var[i]; terms[2 * i + 1] = c.lc_coef[i]; }
+        x->lc_terms.upload(terms);
+        std::vector<uint32_t> aux = c.aux;
+        if (aux.empty()) aux.push_back(0);
+        x->aux.upload(aux);
+        // coefficient table scaled by R: as Montgomery numbers these are just the Montgomery forms
+        std::vector<Fr> cr(c.coefs.size());
+        for (size_t i = 0; i < cr.size(); ++i) cr[i] = Fr::from_u256(c.coefs[i]);
+        x->coef_r.upload(cr);
+        const uint32_t NSMALL = 4096;
+        std::vector<Fr> inv(NSMALL);
+        for (uint32_t i = 0; i < NSMALL; ++i) inv[i] = Fr::from_u64(i);
+        batch_inverse(inv.data(), NSMALL);
+        std::vector<U256> inv_std(NSMALL);
+        for (uint32_t i = 0; i < NSMALL; ++i) inv_std[i] = inv[i].to_u256();
+        x->small_inv.upload(inv_std);
+        dev::DevProgram& P = x->prog;
+        P.ops = (const uint4*)x->ops.p; P.level_ptr = (const uint32_t*)x->level_ptr.p; P.lc_ptr = (const uint32_t*)x->lc_ptr.p;
+        P.lc_terms = (const uint2*)x->lc_terms.p; P.aux = (const uint32_t*)x->aux.p; P.coef_r = x->coef_r.p;
+        P.small_inv = x->small_inv.p; P.n_small_inv = NSMALL;
+        P.n_levels = c.n_levels(); P.n_ops = (uint32_t)c.ops.size(); P.n_vars = c.n_vars; P.n_temps = c.n_temps;
+        P.n_outputs = c.n_outputs; P.n_inputs = c.n_inputs();
+    }
+    // R1CS
+    {
+        auto up_terms = [](const std::vector<uint32_t>& var, const std::vector<uint32_t>& coef, DevBuf& dst) {
+            std::vector<uint32_t> t(2 * var.size() + 2);
+            for (size_t i = 0; i < var.size(); ++i) { t[2 * i] = var[i]; t[2 * i + 1] = coef[i]; }
+            dst.upload(t);
+        };
+        x->a_ptr.upload(c.a_ptr); x->b_ptr.upload(c.b_ptr); x->c_ptr.upload(c.c_ptr);
+        up_terms(c.a_var, c.a_coef, x->a_terms); up_terms(c.b_var, c.b_coef, x->b_terms); up_terms(c.c_var, c.c_coef, x->c_terms);
+        dev::DevR1cs& R = x->r1cs;
+        R.a_ptr = (const uint32_t*)x->a_ptr.p; R.b_ptr = (const uint32_t*)x->b_ptr.p; R.c_ptr = (const uint32_t*)x->c_ptr.p;
+        R.a_terms = (const uint2*)x->a_terms.p; R.b_terms = (const uint2*)x->b_terms.p; R.c_terms = (const uint2*)x->c_terms.p;
+        R.coef_r = x->coef_r.p; R.n_constraints = c.n_constraints; R.n_public = c.n_public(); R.n_vars = c.n_vars;
+    }
+    x->stride = (size_t)c.n_vars + c.n_temps;
+    x->w_all.alloc(x->stride * 32 * max_batch);
+    x->inputs.alloc((size_t)std::max(1u, c.n_inputs()) * 32 * max_batch);
+    x->first_bad.alloc(4 * (size_t)max_batch);
+    x->bad_host.resize(max_batch);
+
+    if (zk) {
+        const unsigned log_n = zk->log_n;
+        const size_t N = (size_t)1 << log_n;
+        // twiddles omega^k, omega^-k (k < N/2) and the bit-reversed coset scale g^j / N
+        const Fr omega = fr_root_of_unity(log_n), omega_inv = omega.inv();
+        const Fr g = fr_root_of_unity(log_n + 1);
+        const Fr n_inv = Fr::from_u64(N).inv();
+        std::vector<Fr> fw(std::max<size_t>(1, N / 2)), iv(std::max<size_t>(1, N / 2)), cs(N);
+        const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t) {
+            th.emplace_back([&, t]() {
+                size_t beg = (N / 2) * t / T, end = (N / 2) * (t + 1) / T;
+                if (beg < end) {
+                    U256 e = {{(uint64_t)beg, 0, 0, 0}};
+                    Fr a = omega.pow(e), b = omega_inv.pow(e);
+                    for (size_t i = beg; i < end; ++i) { fw[i] = a; iv[i] = b; a = a * omega; b = b * omega_inv; }
+                }
+                beg = N * t / T; end = N * (t + 1) / T;
+                if (beg < end) {
+                    U256 e = {{(uint64_t)beg, 0, 0, 0}};
+                    Fr a = g.pow(e) * n_inv;
+                    for (size_t j = beg; j < end; ++j) {
+                        size_t p = 0;
+                        for (unsigned bit = 0; bit < log_n; ++bit) if (j & ((size_t)1 << bit)) p |= (size_t)1 << (log_n - 1 - bit);
+                        cs[p] = a;
+                        a = a * g;
+                    }
+                }
+            });
+        }
+        for (auto& t : th) t.join();
+        if (N == 1) { fw[0] = Fr::one(); iv[0] = Fr::one(); }
+        x->tw_fwd.upload(fw); x->tw_inv.upload(iv); x->coset_scale.upload(cs);
+        x->ntt.tw_fwd = x->tw_fwd.p; x->ntt.tw_inv = x->tw_inv.p; x->ntt.log_n = (int)log_n;
+        x->va.alloc(N * 32); x->vb.alloc(N * 32); x->vc.alloc(N * 32); x->vd.alloc(N * 32);
+        size_t ws = std::max(dev::MsmPlan<dev::Fq>::workspace_bytes(c.n_vars, ZKE_MSM_C_WITNESS),
+                             dev::MsmPlan<dev::Fq>::workspace_bytes((uint32_t)N, ZKE_MSM_C_H));
+        ws = std::max(ws, dev::MsmPlan<dev::Fq2>::workspace_bytes(c.n_vars, ZKE_MSM_C_WITNESS));
+        x->msm_ws.alloc(ws);
+        x->results.alloc((size_t)max_batch * ZKE_RESULT_STRIDE);
+    }
+    CUDA_OK(cudaDeviceSynchronize());
+    return x.release();
+}
+
+static std::string assert_message(const zke_ctx* x, uint32_t email, uint32_t row) {
+    const Circuit& c = x->circuit->c;
+    std::string scope = row < c.scope_of_constraint.size() ? c.scopes[c.scope_of_constraint[row]] : "?";
+    return "Assert Failed: constraint " + std::to_string(row) + " in template " + scope + " @ email " + std::to_string(email);
+}
+
+// Runs the witness kernel for `batch` emails whose inputs are in host memory.
+static void do_witness(zke_ctx* x, const uint8_t* inputs, size_t batch) {
+    const Circuit& c = x->circuit->c;
+    if (batch == 0 || batch > x->max_batch) throw std::runtime_error("batch exceeds the context's max_batch");
+    CUDA_OK(cudaSetDevice(x->device));
+    if (c.n_inputs()) CUDA_OK(cudaMemcpyAsync(x->inputs.p, inputs, (size_t)c.n_inputs() * 32 * batch, cudaMemcpyHostToDevice, x->stream));
+    dev::launch_witness(x->prog, x->w_all.p, x->stride, x->inputs.p, (uint32_t)batch, x->stream);
+    x->loaded = (uint32_t)batch;
+}
+
+// constraint check only (no zkey needed): uses scratch a/b vectors sized to n_constraints
+static int do_check(zke_ctx* x, size_t batch, int32_t* status, std::string& msg) {
+    const Circuit& c = x->circuit->c;
+    const uint32_t rows = c.n_constraints + c.n_public() + 1;
+    DevBuf ta, tb;
+    uint8_t *pa, *pb;
+    if (x->va.p && x->va.bytes >= (size_t)rows * 32) { pa = x->va.p; pb = x->vb.p; }
+    else { ta.alloc((size_t)rows * 32); tb.alloc((size_t)rows * 32); pa = ta.p; pb = tb.p; }
+    CUDA_OK(cudaMemsetAsync(x->first_bad.p, 0xff, 4 * batch, x->stream));
+    for (size_t e = 0; e < batch; ++e) {
+        dev::launch_build_ab(x->r1cs, x->w_all.p + 32 * x->stride * e, pa, pb, rows, (uint32_t*)x->first_bad.p + e, x->stream);
+    }
+    CUDA_OK(cudaMemcpyAsync(x->bad_host.data(), x->first_bad.p, 4 * batch, cudaMemcpyDeviceToHost, x->stream));
+    CUDA_OK(cudaStreamSynchronize(x->stream));
+    int bad = 0;
+    for (size_t e = 0; e < batch; ++e) {
+        int32_t s = x->bad_host[e] == 0xffffffffu ? -1 : (int32_t)x->bad_host[e];
+        if (status) status[e] = s;
+        if (s >= 0) { if (!bad) msg = assert_message(x, (uint32_t)e, (uint32_t)s); ++bad; }
+    }
+    return bad;
+}
+
+template <class F>
+static void read_affine(const uint8_t* xyzz, AffineH<F>& out) {
+    F v[4];
+    memcpy(v, xyzz, sizeof v);
+    out = xyzz_to_affine<F>(v[0], v[1], v[2], v[3]);
+}
+
+static void write_fq(uint8_t* dst, const Fq& x) { U256 s = x.to_u256(); memcpy(dst, s.v, 32); }
+
+static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs_out, uint8_t* publics_out, int32_t* status, std::string& msg) {
+    const Circuit& c = x->circuit->c;
+    const zke_zkey* zk = x->zkey;
+    if (!zk) throw std::runtime_error("context was opened without a proving key");
+    if (batch == 0 || batch > x->loaded) throw std::runtime_error("no witness loaded for this batch (call zke_witness first)");
+    CUDA_OK(cudaSetDevice(x->device));
+    const uint32_t N = 1u << zk->log_n, m = c.n_vars, l = c.n_public();
+    cudaStream_t st = x->stream;
+    CUDA_OK(cudaMemsetAsync(x->first_bad.p, 0xff, 4 * batch, st));
+    for (size_t e = 0; e < batch; ++e) {
+        const uint8_t* w = x->w_all.p + 32 * x->stride * e;
+        uint8_t* res = x->results.p + ZKE_RESULT_STRIDE * e;
+        dev::launch_build_ab(x->r1cs, w, x->va.p, x->vb.p, N, (uint32_t*)x->first_bad.p + e, st);
+        dev::launch_hadamard(x->va.p, x->vb.p, x->vc.p, N, st);
+        dev::launch_intt_dif(x->va.p, x->ntt, x->coset_scale.p, st);
+        dev::launch_intt_dif(x->vb.p, x->ntt, x->coset_scale.p, st);
+        dev::launch_intt_dif(x->vc.p, x->ntt, x->coset_scale.p, st);
+        dev::launch_ntt_dit(x->va.p, x->ntt, st);
+        dev::launch_ntt_dit(x->vb.p, x->ntt, st);
+        dev::launch_ntt_dit(x->vc.p, x->ntt, st);
+        dev::launch_quotient(x->va.p, x->vb.p, x->vc.p, x->vd.p, N, st);
+        dev::MsmPlan<dev::Fq>::run(zk->A.p, w, m, ZKE_MSM_C_WITNESS, true, x->msm_ws.p, res + 0, st);
+        dev::MsmPlan<dev::Fq>::run(zk->B1.p, w, m, ZKE_MSM_C_WITNESS, true, x->msm_ws.p, res + 128, st);
+        dev::MsmPlan<dev::Fq>::run(zk->C.p, w, m, ZKE_MSM_C_WITNESS, true, x->msm_ws.p, res + 256, st);
+        dev::MsmPlan<dev::Fq>::run(zk->H.p, x->vd.p, N, ZKE_MSM_C_H, false, x->msm_ws.p, res + 384, st);
+        dev::MsmPlan<dev::Fq2>::run(zk->B2.p, w, m, ZKE_MSM_C_WITNESS, true, x->msm_ws.p, res + 512, st);
+    }
+    std::vector<uint8_t> res_host(ZKE_RESULT_STRIDE * batch);
+    std::vector<uint8_t> pub_host((size_t)std::max(1u, l) * 32 * batch);
+    CUDA_OK(cudaMemcpyAsync(res_host.data(), x->results.p, res_host.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(x->bad_host.data(), x->first_bad.p, 4 * batch, cudaMemcpyDeviceToHost, st));
+    if (l) CUDA_OK(cudaMemcpy2DAsync(pub_host.data(), (size_t)l * 32, x->w_all.p + 32, x->stride * 32, (size_t)l * 32, batch, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+
+    int bad = 0;
+    const G1JacH alpha1 = G1JacH::from_affine(zk->alpha1), beta1 = G1JacH::from_affine(zk->beta1), delta1 = G1JacH::from_affine(zk->delta1);
+    const G2JacH beta2 = G2JacH::from_affine(zk->beta2), delta2 = G2JacH::from_affine(zk->delta2);
+    for (size_t e = 0; e < batch; ++e) {
+        int32_t s = x->bad_host[e] == 0xffffffffu ? -1 : (int32_t)x->bad_host[e];
+        if (status) status[e] = s;
+        uint8_t* out = proofs_out + 256 * e;
+        if (s >= 0) {
+            if (!bad) msg = assert_message(x, (uint32_t)e, (uint32_t)s);
+            ++bad;
+            memset(out, 0, 256);
+            continue;
+        }
+        U256 r, sc;
+        if (rs) { memcpy(r.v, rs + 64 * e, 32); memcpy(sc.v, rs + 64 * e + 32, 32); }
+        else { random_scalar(r); random_scalar(sc); }
+        if (u256_cmp(r, fr_params().p) >= 0 || u256_cmp(sc, fr_params().p) >= 0) throw std::runtime_error("r / s not reduced mod the group order");
+        const uint8_t* res = res_host.data() + ZKE_RESULT_STRIDE * e;
+        G1AffineH ma, mb1, mc, mh;
+        G2AffineH mb2;
+        read_affine<Fq>(res + 0, ma); read_affine<Fq>(res + 128, mb1); read_affine<Fq>(res + 256, mc); read_affine<Fq>(res + 384, mh);
+        read_affine<Fq2>(res + 512, mb2);
+        // pi_A = alpha + A + r delta ; pi_B = beta + B + s delta ; pi_C = C + H + s pi_A + r pi_B1 - r s delta
+        G1JacH pa = alpha1.add(G1JacH::from_affine(ma)).add(delta1.mul(r));
+        G2JacH pb2 = beta2.add(G2JacH::from_affine(mb2)).add(delta2.mul(sc));
+        G1JacH pb1 = beta1.add(G1JacH::from_affine(mb1)).add(delta1.mul(sc));
+        U256 rs_prod = (Fr::from_u256(r) * Fr::from_u256(sc)).to_u256();
+        G1JacH pc = G1JacH::from_affine(mc).add(G1JacH::from_affine(mh)).add(pa.mul(sc)).add(pb1.mul(r)).add(delta1.mul(rs_prod).neg());
+        G1AffineH A = pa.to_affine(), C = pc.to_affine();
+        G2AffineH B = pb2.to_affine();
+        write_fq(out + 0, A.x); write_fq(out + 32, A.y);
+        write_fq(out + 64, B.x.c0); write_fq(out + 96, B.x.c1); write_fq(out + 128, B.y.c0); write_fq(out + 160, B.y.c1);
+        write_fq(out + 192, C.x); write_fq(out + 224, C.y);
+    }
+    if (publics_out && l) memcpy(publics_out, pub_host.data(), (size_t)l * 32 * batch);
+    return bad;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int zke_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+zke_zkey* zke_setup(const zke_circuit* c, uint64_t seed, int device, char* err, size_t errcap) {
+    try { if (!c) throw std::runtime_error("null circuit"); return do_setup(c, seed, device); }
+    catch (const std::exception& e) { set_err(err, errcap, e.what()); return nullptr; }
+}
+void zke_zkey_free(zke_zkey* z) { if (z) { cudaSetDevice(z->device); delete z; } }
+
+int zke_zkey_info(const zke_zkey* z, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_log2) {
+    if (!z) return -1;
+    if (n_vars) *n_vars = z->n_vars;
+    if (n_public) *n_public = z->n_public;
+    if (domain_log2) *domain_log2 = z->log_n;
+    return 0;
+}
+
+// Copies one section of the proving key to the host as affine points with standard-form little-endian
+// coordinates (G1: x, y = 64 bytes; G2: x.c0, x.c1, y.c0, y.c1 = 128 bytes); infinity = all zero.
+int64_t zke_zkey_section(const zke_zkey* z, int section, uint8_t* out, size_t cap) {
+    if (!z) return -1;
+    try {
+        CUDA_OK(cudaSetDevice(z->device));
+        const size_t N = (size_t)1 << z->log_n;
+        auto g1_host = [&](const G1AffineH* pts, size_t n) -> int64_t {
+            if (!out) return (int64_t)n;
+            if (cap < n * 64) return -2;
+            for (size_t i = 0; i < n; ++i) { write_fq(out + 64 * i, pts[i].x); write_fq(out + 64 * i + 32, pts[i].y); }
+            return (int64_t)n;
+        };
+        auto g1_dev = [&](const DevBuf& b, size_t n) -> int64_t {
+            if (!out) return (int64_t)n;
+            std::vector<G1AffineH> h(n);
+            CUDA_OK(cudaMemcpy(h.data(), b.p, n * sizeof(G1AffineH), cudaMemcpyDeviceToHost));
+            return g1_host(h.data(), n);
+        };
+        auto g2_host = [&](const G2AffineH* pts, size_t n) -> int64_t {
+            if (!out) return (int64_t)n;
+            if (cap < n * 128) return -2;
+            for (size_t i = 0; i < n; ++i) {
+                write_fq(out + 128 * i, pts[i].x.c0); write_fq(out + 128 * i + 32, pts[i].x.c1);
+                write_fq(out + 128 * i + 64, pts[i].y.c0); write_fq(out + 128 * i + 96, pts[i].y.c1);
+            }
+            return (int64_t)n;
+        };
+        switch (section) {
+            case ZKE_SEC_ALPHA1: return g1_host(&z->alpha1, 1);
+            case ZKE_SEC_BETA1: return g1_host(&z->beta1, 1);
+            case ZKE_SEC_DELTA1: return g1_host(&z->delta1, 1);
+            case ZKE_SEC_BETA2: return g2_host(&z->beta2, 1);
+            case ZKE_SEC_GAMMA2: return g2_host(&z->gamma2, 1);
+            case ZKE_SEC_DELTA2: return g2_host(&z->delta2, 1);
+            case ZKE_SEC_IC: return g1_host(z->ic.data(), z->ic.size());
+            case ZKE_SEC_A: return g1_dev(z->A, z->n_vars);
+            case ZKE_SEC_B1: return g1_dev(z->B1, z->n_vars);
+            case ZKE_SEC_C: return g1_dev(z->C, z->n_vars);
+            case ZKE_SEC_H: return g1_dev(z->H, N);
+            case ZKE_SEC_B2: {
+                if (!out) return z->n_vars;
+                std::vector<G2AffineH> h(z->n_vars);
+                CUDA_OK(cudaMemcpy(h.data(), z->B2.p, h.size() * sizeof(G2AffineH), cudaMemcpyDeviceToHost));
+                return g2_host(h.data(), h.size());
+            }
+            default: return -1;
+        }
+    } catch (const std::exception&) { return -3; }
+}
+
+zke_ctx* zke_ctx_open(const zke_circuit* c, const zke_zkey* zkey, int device, uint32_t max_batch, char* err, size_t errcap) {
+    try { if (!c) throw std::runtime_error("null circuit"); return do_open(c, zkey, device, max_batch); }
+    catch (const std::exception& e) { set_err(err, errcap, e.what()); return nullptr; }
+}
+void zke_ctx_close(zke_ctx* x) {
+    if (!x) return;
+    cudaSetDevice(x->device);
+    if (x->stream) cudaStreamDestroy(x->stream);
+    delete x;
+}
+void* zke_ctx_stream(const zke_ctx* x) { return x ? (void*)x->stream : nullptr; }
+uint64_t zke_kernel_launches(void) { return dev::g_kernel_launches; }
+
+int zke_witness(zke_ctx* x, const uint8_t* inputs, size_t batch, uint8_t* wtns_out, int32_t* status, char* err, size_t errcap) {
+    try {
+        if (!x) throw std::runtime_error("null context");
+        do_witness(x, inputs, batch);
+        std::string msg;
+        int bad = do_check(x, batch, status, msg);
+        if (wtns_out) {
+            const size_t m = x->circuit->c.n_vars;
+            CUDA_OK(cudaMemcpy2D(wtns_out, m * 32, x->w_all.p, x->stride * 32, m * 32, batch, cudaMemcpyDeviceToHost));
+        }
+        if (bad) { set_err(err, errcap, msg); return bad; }
+        return 0;
+    } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+
+int zke_load_witness(zke_ctx* x, const uint8_t* wtns, size_t batch, char* err, size_t errcap) {
+    try {
+        if (!x) throw std::runtime_error("null context");
+        if (batch == 0 || batch > x->max_batch) throw std::runtime_error("batch exceeds the context's max_batch");
+        CUDA_OK(cudaSetDevice(x->device));
+        const size_t m = x->circuit->c.n_vars;
+        CUDA_OK(cudaMemcpy2D(x->w_all.p, x->stride * 32, wtns, m * 32, m * 32, batch, cudaMemcpyHostToDevice));
+        x->loaded = (uint32_t)batch;
+        return 0;
+    } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+
+int zke_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs_out, uint8_t* publics_out, int32_t* status, char* err, size_t errcap) {
+    try {
+        if (!x || !proofs_out) throw std::runtime_error("null argument");
+        std::string msg;
+        int bad = do_prove(x, batch, rs, proofs_out, publics_out, status, msg);
+        if (bad) { set_err(err, errcap, msg); return bad; }
+        return 0;
+    } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+
+int zke_fullprove(zke_ctx* x, const uint8_t* inputs, size_t batch, const uint8_t* rs, uint8_t* proofs_out, uint8_t* publics_out,
+                  int32_t* status, char* err, size_t errcap) {
+    try {
+        if (!x || !proofs_out) throw std::runtime_error("null argument");
+        do_witness(x, inputs, batch);
+        std::string msg;
+        int bad = do_prove(x, batch, rs, proofs_out, publics_out, status, msg);
+        if (bad) { set_err(err, errcap, msg); return bad; }
+        return 0;
+    } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// Device-side BN254 prime-field arithmetic for sm_100a: 8 x 32-bit limbs, Montgomery form (R = 2^256),
+// carry chains written with mad.lo/hi.cc PTX (IMAD pipe; B300_MICROARCH "Pipe rates": IMAD 64/clk/SM).
+// Memory image of an element = 32 bytes little-endian, identical to the host's U256.
+//
+// Role in the reference: the Fr/Fq layer of wasmcurves 0.2.0 (un-vendored; /root/reference/yarn.lock:8521-8525)
+// that snarkjs' prover and circom's witness calculator run on.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace zke {
+namespace dev {
+
+struct FieldConsts {
+    uint32_t mod[8];
+    uint32_t r[8];    // 2^256 mod p  (Montgomery one)
+    uint32_t r2[8];   // 2^512 mod p
+    uint32_t inv;     // -p^-1 mod 2^32
+};
+// Defined here: all device code is compiled as ONE translation unit (engine.cu includes the kernel files).
+__constant__ FieldConsts FR_C;
+__constant__ FieldConsts FQ_C;
+
+struct FrTag { static __device__ __forceinline__ const FieldConsts& C() { return FR_C; } };
+struct FqTag { static __device__ __forceinline__ const FieldConsts& C() { return FQ_C; } };
+
+// ---- carry-chain primitives --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+
+template <class Tag>
+struct Fp {
+    uint32_t v[8];
+
+    static __device__ __forceinline__ Fp zero() { Fp r; for (int i = 0; i < 8; ++i) r.v[i] = 0; return r; }
+    static __device__ __forceinline__ Fp one() { Fp r; for (int i = 0; i < 8; ++i) r.v[i] = Tag::C().r[i]; return r; }
+    static __device__ __forceinline__ Fp r2() { Fp r; for (int i = 0; i < 8; ++i) r.v[i] = Tag::C().r2[i]; return r; }
+    static __device__ __forceinline__ Fp load(const void* p) {  // 32-byte aligned global / shared address
+        Fp r;
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+        uint4 a = q[0], b = q[1];
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+        return r;
+    }
+    __device__ __forceinline__ void store(void* p) const {
+        uint4* q = reinterpret_cast<uint4*>(p);
+        q[0] = make_uint4(v[0], v[1], v[2], v[3]);
+        q[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    }
+    __device__ __forceinline__ bool is_zero() const { return (v[0] | v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7]) == 0; }
+    __device__ __forceinline__ bool operator==(const Fp& o) const {
+        uint32_t d = 0;
+        for (int i = 0; i < 8; ++i) d |= v[i] ^ o.v[i];
+        return d == 0;
+    }
+    __device__ __forceinline__ bool operator!=(const Fp& o) const { return !(*this == o); }
+
+    // r = a - p if a >= p (a < 2p)
+    __device__ __forceinline__ void reduce_once() {
+        const FieldConsts& C = Tag::C();
+        uint32_t t[8];
+        t[0] = sub_cc(v[0], C.mod[0]);
+#pragma unroll
+        for (int i = 1; i < 8; ++i) t[i] = subc_cc(v[i], C.mod[i]);
+        uint32_t borrow = subc(0, 0);  // 0xffffffff if a < p
+        if (borrow == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = t[i];
+        }
+    }
+
+    friend __device__ __forceinline__ Fp operator+(const Fp& a, const Fp& b) {
+        Fp r;
+        r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < 8; ++i) r.v[i] = addc_cc(a.v[i], b.v[i]);
+        // p < 2^254: no carry out of 256 bits
+        r.reduce_once();
+        return r;
+    }
+    friend __device__ __forceinline__ Fp operator-(const Fp& a, const Fp& b) {
+        const FieldConsts& C = Tag::C();
+        Fp r;
+        r.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+        for (int i = 1; i < 8; ++i) r.v[i] = subc_cc(a.v[i], b.v[i]);
+        uint32_t borrow = subc(0, 0);
+        if (borrow) {
+            r.v[0] = add_cc(r.v[0], C.mod[0]);
+#pragma unroll
+            for (int i = 1; i < 7; ++i) r.v[i] = addc_cc(r.v[i], C.mod[i]);
+            r.v[7] = addc(r.v[7], C.mod[7]);
+        }
+        return r;
+    }
+    __device__ __forceinline__ Fp neg() const { return is_zero() ? *this : (zero() - *this); }
+    __device__ __forceinline__ Fp dbl() const { return *this + *this; }
+
+    // Montgomery product a*b/2^256 mod p (CIOS, operands < p, p < 2^254 so 9 words suffice)
+    friend __device__ __forceinline__ Fp operator*(const Fp& a, const Fp& b) {
+        const FieldConsts& C = Tag::C();
+        uint32_t t[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) t[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t bi = b.v[i];
+            // t += a * bi  (low halves, then high halves)
+            t[0] = mad_lo_cc(a.v[0], bi, t[0]);
+#pragma unroll
+            for (int j = 1; j < 8; ++j) t[j] = madc_lo_cc(a.v[j], bi, t[j]);
+            t[8] = addc(t[8], 0);
+            t[1] = mad_hi_cc(a.v[0], bi, t[1]);
+#pragma unroll
+            for (int j = 1; j < 7; ++j) t[j + 1] = madc_hi_cc(a.v[j], bi, t[j + 1]);
+            t[8] = madc_hi_cc(a.v[7], bi, t[8]);   // cannot carry out: t < 2^288
+            // t = (t + m*p) / 2^32
+            const uint32_t m = t[0] * C.inv;
+            (void)mad_lo_cc(m, C.mod[0], t[0]);
+#pragma unroll
+            for (int j = 1; j < 8; ++j) t[j] = madc_lo_cc(m, C.mod[j], t[j]);
+            t[8] = addc(t[8], 0);
+            t[0] = mad_hi_cc(m, C.mod[0], t[1]);
+#pragma unroll
+            for (int j = 1; j < 7; ++j) t[j] = madc_hi_cc(m, C.mod[j], t[j + 1]);
+            t[7] = madc_hi_cc(m, C.mod[7], t[8]);
+            t[8] = addc(0, 0);
+        }
+        Fp r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = t[i];
+        r.reduce_once();
+        return r;
+    }
+    __device__ __forceinline__ Fp sqr() const { return *this * *this; }
+    __device__ __forceinline__ Fp to_mont() const { return *this * r2(); }
+    __device__ __forceinline__ Fp from_mont() const {
+        Fp o = zero(); o.v[0] = 1;
+        return *this * o;
+    }
+    // Fermat inverse (Montgomery in/out); inv(0) = 0.  ~380 products - use sparingly / batch.
+    __device__ Fp inv() const {
+        const FieldConsts& C = Tag::C();
+        uint32_t e[8];
+        e[0] = sub_cc(C.mod[0], 2);
+#pragma unroll
+        for (int i = 1; i < 8; ++i) e[i] = subc_cc(C.mod[i], 0);
+        Fp res = one(), base = *this;
+        for (int w = 7; w >= 0; --w) {
+            for (int bit = 31; bit >= 0; --bit) {
+                res = res.sqr();
+                if ((e[w] >> bit) & 1) res = res * base;
+            }
+        }
+        return res;
+    }
+};
+
+typedef Fp<FrTag> Fr;
+typedef Fp<FqTag> Fq;
+
+// Fq2 = Fq[u]/(u^2+1)
+struct Fq2 {
+    Fq c0, c1;
+    static __device__ __forceinline__ Fq2 zero() { Fq2 r; r.c0 = Fq::zero(); r.c1 = Fq::zero(); return r; }
+    static __device__ __forceinline__ Fq2 one() { Fq2 r; r.c0 = Fq::one(); r.c1 = Fq::zero(); return r; }
+    static __device__ __forceinline__ Fq2 load(const void* p) { Fq2 r; r.c0 = Fq::load(p); r.c1 = Fq::load((const char*)p + 32); return r; }
+    __device__ __forceinline__ void store(void* p) const { c0.store(p); c1.store((char*)p + 32); }
+    __device__ __forceinline__ bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    __device__ __forceinline__ bool operator==(const Fq2& o) const { return c0 == o.c0 && c1 == o.c1; }
+    friend __device__ __forceinline__ Fq2 operator+(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; return r; }
+    friend __device__ __forceinline__ Fq2 operator-(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; return r; }
+    friend __device__ __forceinline__ Fq2 operator*(const Fq2& a, const Fq2& b) {
+        Fq t0 = a.c0 * b.c0, t1 = a.c1 * b.c1;
+        Fq2 r;
+        r.c1 = (a.c0 + a.c1) * (b.c0 + b.c1) - t0 - t1;
+        r.c0 = t0 - t1;
+        return r;
+    }
+    __device__ __forceinline__ Fq2 sqr() const {
+        Fq2 r;
+        Fq t = c0 * c1;
+        r.c0 = (c0 + c1) * (c0 - c1);
+        r.c1 = t + t;
+        return r;
+    }
+    __device__ __forceinline__ Fq2 neg() const { Fq2 r; r.c0 = c0.neg(); r.c1 = c1.neg(); return r; }
+    __device__ __forceinline__ Fq2 dbl() const { return *this + *this; }
+    __device__ Fq2 inv() const {
+        Fq d = (c0.sqr() + c1.sqr()).inv();
+        Fq2 r; r.c0 = c0 * d; r.c1 = (c1 * d).neg();
+        return r;
+    }
+};
+
+}  // namespace dev
+}  // namespace zke

@@ -1,0 +1,343 @@
+// Multi-scalar multiplication over BN254 G1 / G2 for the Groth16 prover (pi_A, pi_B, pi_B1, pi_C, H - snarkjs
+// groth16_prove step 5; the reference's implementation is wasmcurves' chunked `multiExpAffine`).
+//
+// Pipeline (all on one stream, no host synchronisation inside):
+//   classify   : scalars 0 / points at infinity are dropped, scalars == 1 go to a "ones" list that is summed by a
+//                plain tree reduction (>= 90 % of EmailVerifier witness scalars are bits), the rest
+//                go to the Pippenger list.
+//   pippenger  : signed c-bit digits -> histogram -> exclusive scan -> scatter of point indices by bucket
+//                (counting sort, no comparison sort) -> buckets cut into chunks of at most CHUNK entries so that a
+//                heavy bucket (small-valued witness scalars pile into few buckets) is spread over many threads ->
+//                per-chunk XYZZ accumulation with coalesced 32/64-byte affine point loads -> per-group running sums
+//                -> per-window tree reduction -> Horner over windows.
+// The accumulation kernels are bound by the integer (IMAD) pipe, not HBM: one mixed addition is 10 Fq products
+// (~300 IMAD each) per 64-byte point (SURVEY 8(d) "Which roofline bounds what").
+#include "device_engine.cuh"
+#include "msm.cuh"
+
+namespace zke {
+namespace dev {
+
+static const int CHUNK = 256;       // max entries accumulated by one thread
+static const int GROUP = 64;        // buckets per running-sum thread
+static const int LIST_FANIN = 32;   // points summed per thread in the list reductions
+
+__device__ __forceinline__ Fr load_scalar(const uint8_t* scalars, uint32_t i) { return Fr::load(scalars + 32ull * i); }
+
+// ---------------------------------------------------------------- classify
+template <class F>
+__global__ void classify_kernel(const uint8_t* __restrict__ points, const uint8_t* __restrict__ scalars, uint32_t n,
+                                uint32_t* ones_list, uint32_t* gen_list, uint32_t* counters /* [0]=ones, [1]=general */) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s = load_scalar(scalars, i);
+    if (s.is_zero()) return;
+    Affine<F> p = Affine<F>::load(points + sizeof(Affine<F>) * (size_t)i);
+    if (p.is_inf()) return;
+    bool one = s.v[0] == 1 && (s.v[1] | s.v[2] | s.v[3] | s.v[4] | s.v[5] | s.v[6] | s.v[7]) == 0;
+    if (one) ones_list[atomicAdd(&counters[0], 1u)] = i;
+    else gen_list[atomicAdd(&counters[1], 1u)] = i;
+}
+
+// ---------------------------------------------------------------- list sums
+// out[t] = sum of points[list[t*FANIN .. )]   (list == nullptr: identity)
+template <class F>
+__global__ void sum_affine_list_kernel(const uint8_t* __restrict__ points, const uint32_t* __restrict__ list,
+                                       const uint32_t* __restrict__ count_ptr, uint32_t count_fixed, uint8_t* out) {
+    const uint32_t count = count_ptr ? *count_ptr : count_fixed;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_out = max(1u, (count + LIST_FANIN - 1) / LIST_FANIN);   // slot 0 is always written
+    if (t >= n_out) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    // strided assignment keeps a warp's point loads close together
+    for (uint32_t k = t; k < count; k += n_out) {
+        uint32_t idx = list ? list[k] : k;
+        acc.madd(Affine<F>::load(points + sizeof(Affine<F>) * (size_t)idx), false);
+    }
+    acc.store(out + sizeof(XYZZ<F>) * (size_t)t);
+}
+
+// in-place tree step: out[t] = sum_{k = t, t + n_out, ...} in[k]
+template <class F>
+__global__ void sum_xyzz_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ count_ptr, uint32_t count_fixed,
+                                uint32_t div, uint8_t* out) {
+    uint32_t count = count_ptr ? *count_ptr : count_fixed;
+    for (uint32_t d = 0; d < div; ++d) count = max(1u, (count + LIST_FANIN - 1) / LIST_FANIN);   // size of `in`
+    const uint32_t n_out = max(1u, (count + LIST_FANIN - 1) / LIST_FANIN);
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_out) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    for (uint32_t k = t; k < count; k += n_out) acc.add(XYZZ<F>::load(in + sizeof(XYZZ<F>) * (size_t)k));
+    acc.store(out + sizeof(XYZZ<F>) * (size_t)t);
+}
+
+// ---------------------------------------------------------------- digits
+struct Digits {
+    int c, n_windows;
+    uint32_t half;   // 2^(c-1) buckets per window
+};
+
+__device__ __forceinline__ uint32_t window_bits(const Fr& s, int bit, int c) {
+    const int w = bit >> 5, b = bit & 31;
+    uint64_t two = s.v[w];
+    if (w + 1 < 8) two |= (uint64_t)s.v[w + 1] << 32;
+    return (uint32_t)((two >> b) & ((1u << c) - 1));
+}
+
+// calls f(window, bucket_in_window, negative) for every non-zero signed digit
+template <class Fn>
+__device__ __forceinline__ void for_each_digit(const Fr& s, const Digits& D, Fn f) {
+    uint32_t carry = 0;
+    for (int j = 0; j < D.n_windows; ++j) {
+        uint32_t raw = window_bits(s, j * D.c, D.c) + carry;
+        if (raw > D.half) {                      // digit = raw - 2^c  (negative), carry 1
+            carry = 1;
+            f(j, (1u << D.c) - raw - 1, true);
+        } else {
+            carry = 0;
+            if (raw) f(j, raw - 1, false);
+        }
+    }
+}
+
+__global__ void digit_hist_kernel(const uint8_t* __restrict__ scalars, const uint32_t* __restrict__ list,
+                                  const uint32_t* __restrict__ count_ptr, uint32_t count_fixed, Digits D, uint32_t* hist) {
+    const uint32_t count = count_ptr ? *count_ptr : count_fixed;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        const uint32_t idx = list ? list[t] : t;
+        Fr s = load_scalar(scalars, idx);
+        for_each_digit(s, D, [&](int j, uint32_t b, bool) { atomicAdd(&hist[(uint32_t)j * D.half + b], 1u); });
+    }
+}
+
+__global__ void digit_scatter_kernel(const uint8_t* __restrict__ scalars, const uint32_t* __restrict__ list,
+                                     const uint32_t* __restrict__ count_ptr, uint32_t count_fixed, Digits D,
+                                     const uint32_t* __restrict__ offsets, uint32_t* cursor, uint32_t* entries) {
+    const uint32_t count = count_ptr ? *count_ptr : count_fixed;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
+        const uint32_t idx = list ? list[t] : t;
+        Fr s = load_scalar(scalars, idx);
+        for_each_digit(s, D, [&](int j, uint32_t b, bool neg) {
+            const uint32_t bucket = (uint32_t)j * D.half + b;
+            const uint32_t pos = offsets[bucket] + atomicAdd(&cursor[bucket], 1u);
+            entries[pos] = idx | (neg ? 0x80000000u : 0u);
+        });
+    }
+}
+
+// ---------------------------------------------------------------- single-block exclusive scan (n up to a few million)
+// out[i] = sum_{k<i} f(in[k]); out[n] = total.  f = identity (mode 0) or ceil(x / CHUNK) (mode 1)
+__global__ void __launch_bounds__(1024) scan_kernel(const uint32_t* __restrict__ in, uint32_t n, int mode, uint32_t* out) {
+    __shared__ uint32_t sums[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t beg = tid * per, end = min(n, beg + per);
+    uint32_t local = 0;
+    for (uint32_t i = beg; i < end; ++i) { uint32_t v = in[i]; local += mode ? (v + CHUNK - 1) / CHUNK : v; }
+    sums[tid] = local;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+        uint32_t v = tid >= off ? sums[tid - off] : 0;
+        __syncthreads();
+        sums[tid] += v;
+        __syncthreads();
+    }
+    uint32_t run = sums[tid] - local;
+    for (uint32_t i = beg; i < end; ++i) { uint32_t v = in[i]; out[i] = run; run += mode ? (v + CHUNK - 1) / CHUNK : v; }
+    if (tid == 1023) out[n] = sums[1023];
+}
+
+__global__ void fill_work_kernel(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off, uint32_t n_buckets,
+                                 uint32_t* work_bucket) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    const uint32_t nch = (hist[b] + CHUNK - 1) / CHUNK;
+    for (uint32_t i = 0; i < nch; ++i) work_bucket[chunk_off[b] + i] = b;
+}
+
+// one thread per chunk: partial[w] = sum of (+/-) points of the chunk
+template <class F>
+__global__ void __launch_bounds__(128)
+chunk_sum_kernel(const uint8_t* __restrict__ points, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
+                 const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off, const uint32_t* __restrict__ work_bucket,
+                 uint32_t n_buckets, uint8_t* partial) {
+    const uint32_t total = chunk_off[n_buckets];
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+        const uint32_t b = work_bucket[w];
+        const uint32_t ci = w - chunk_off[b];
+        const uint32_t beg = offsets[b] + ci * CHUNK;
+        const uint32_t end = min(offsets[b] + hist[b], beg + CHUNK);
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t k = beg; k < end; ++k) {
+            const uint32_t e = entries[k];
+            acc.madd(Affine<F>::load(points + sizeof(Affine<F>) * (size_t)(e & 0x7fffffffu)), (e >> 31) != 0);
+        }
+        acc.store(partial + sizeof(XYZZ<F>) * (size_t)w);
+    }
+}
+
+// one thread per GROUP consecutive buckets of one window: sum_b (b+1) B_b restricted to the group, as
+// T + first_index * S with T the in-group weighted sum and S the plain sum
+template <class F>
+__global__ void __launch_bounds__(128)
+group_sum_kernel(const uint8_t* __restrict__ partial, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off,
+                 uint32_t half, uint32_t n_groups_total, uint8_t* group_out) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups_total) return;
+    const uint32_t groups_per_window = (half + GROUP - 1) / GROUP;
+    const uint32_t window = g / groups_per_window, gi = g % groups_per_window;
+    const uint32_t lo = gi * GROUP, hi = min(half, lo + GROUP);
+    XYZZ<F> running = XYZZ<F>::inf(), total = XYZZ<F>::inf();
+    for (uint32_t b = hi; b-- > lo;) {
+        const uint32_t bucket = window * half + b;
+        const uint32_t nch = (hist[bucket] + CHUNK - 1) / CHUNK;
+        for (uint32_t i = 0; i < nch; ++i) running.add(XYZZ<F>::load(partial + sizeof(XYZZ<F>) * (size_t)(chunk_off[bucket] + i)));
+        total.add(running);
+    }
+    // total = sum (b - lo + 1) B_b ; add lo * running  (lo < 2^15)
+    if (lo && !running.is_inf()) {
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (int bit = 31 - __clz(lo); bit >= 0; --bit) {
+            acc.dbl();
+            if ((lo >> bit) & 1) acc.add(running);
+        }
+        total.add(acc);
+    }
+    total.store(group_out + sizeof(XYZZ<F>) * (size_t)g);
+}
+
+// one block per window: tree-reduce the window's group sums in place (global memory), result in slot 0
+template <class F>
+__global__ void __launch_bounds__(512)
+window_reduce_kernel(uint8_t* group_out, uint32_t groups_per_window) {
+    uint8_t* base = group_out + sizeof(XYZZ<F>) * (size_t)blockIdx.x * groups_per_window;
+    uint32_t n = groups_per_window;
+    while (n > 1) {
+        const uint32_t halfn = (n + 1) / 2;
+        for (uint32_t t = threadIdx.x; t + halfn < n; t += blockDim.x) {
+            XYZZ<F> a = XYZZ<F>::load(base + sizeof(XYZZ<F>) * (size_t)t);
+            a.add(XYZZ<F>::load(base + sizeof(XYZZ<F>) * (size_t)(t + halfn)));
+            a.store(base + sizeof(XYZZ<F>) * (size_t)t);
+        }
+        __syncthreads();
+        n = halfn;
+    }
+}
+
+// result = ones_sum + sum_j 2^(c j) window_j
+template <class F>
+__global__ void msm_final_kernel(const uint8_t* __restrict__ group_out, uint32_t groups_per_window, Digits D,
+                                 const uint8_t* __restrict__ ones_sum, int have_pippenger, uint8_t* result) {
+    if (threadIdx.x || blockIdx.x) return;
+    XYZZ<F> acc = XYZZ<F>::inf();
+    if (have_pippenger) {
+        for (int j = D.n_windows - 1; j >= 0; --j) {
+            for (int k = 0; k < D.c; ++k) acc.dbl();
+            acc.add(XYZZ<F>::load(group_out + sizeof(XYZZ<F>) * (size_t)j * groups_per_window));
+        }
+    }
+    if (ones_sum) acc.add(XYZZ<F>::load(ones_sum));
+    acc.store(result);
+}
+
+// ---------------------------------------------------------------- host orchestration
+template <class F>
+size_t MsmPlan<F>::workspace_bytes(uint32_t n, int c) {
+    const int W = (255 + c - 1) / c;
+    const size_t half = (size_t)1 << (c - 1);
+    const size_t n_buckets = half * W;
+    const size_t max_entries = (size_t)n * W;
+    const size_t max_chunks = n_buckets + max_entries / CHUNK + 1;
+    const size_t groups = ((half + GROUP - 1) / GROUP) * W;
+    size_t b = 0;
+    auto al = [&](size_t x) { b += (x + 255) & ~(size_t)255; };
+    al(4 * 2);                         // counters
+    al(4 * (size_t)n);                 // ones list
+    al(4 * (size_t)n);                 // general list
+    al(4 * (n_buckets + 1));           // hist
+    al(4 * (n_buckets + 1));           // offsets
+    al(4 * (n_buckets + 1));           // cursor
+    al(4 * (n_buckets + 1));           // chunk_off
+    al(4 * max_entries);               // entries
+    al(4 * max_chunks);                // work_bucket
+    al(sizeof(XYZZ<F>) * max_chunks);  // partial
+    al(sizeof(XYZZ<F>) * groups);      // group sums
+    al(sizeof(XYZZ<F>) * ((size_t)n / LIST_FANIN + 2) * 2);  // list reduction ping-pong
+    return b;
+}
+
+template <class F>
+void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, int c, bool classify, uint8_t* ws,
+                     uint8_t* result, cudaStream_t st) {
+    Digits D;
+    D.c = c;
+    D.n_windows = (255 + c - 1) / c;
+    D.half = 1u << (c - 1);
+    const uint32_t n_buckets = D.half * D.n_windows;
+    const size_t max_entries = (size_t)n * D.n_windows;
+    const size_t max_chunks = n_buckets + max_entries / CHUNK + 1;
+    const uint32_t groups_per_window = (D.half + GROUP - 1) / GROUP;
+    const uint32_t groups = groups_per_window * D.n_windows;
+    uint8_t* p = ws;
+    auto take = [&](size_t x) { uint8_t* r = p; p += (x + 255) & ~(size_t)255; return r; };
+    uint32_t* counters = (uint32_t*)take(8);
+    uint32_t* ones_list = (uint32_t*)take(4 * (size_t)n);
+    uint32_t* gen_list = (uint32_t*)take(4 * (size_t)n);
+    uint32_t* hist = (uint32_t*)take(4 * ((size_t)n_buckets + 1));
+    uint32_t* offsets = (uint32_t*)take(4 * ((size_t)n_buckets + 1));
+    uint32_t* cursor = (uint32_t*)take(4 * ((size_t)n_buckets + 1));
+    uint32_t* chunk_off = (uint32_t*)take(4 * ((size_t)n_buckets + 1));
+    uint32_t* entries = (uint32_t*)take(4 * max_entries);
+    uint32_t* work_bucket = (uint32_t*)take(4 * max_chunks);
+    uint8_t* partial = take(sizeof(XYZZ<F>) * max_chunks);
+    uint8_t* group_out = take(sizeof(XYZZ<F>) * groups);
+    const size_t list_slots = (size_t)n / LIST_FANIN + 2;
+    uint8_t* red_a = take(sizeof(XYZZ<F>) * list_slots);
+    uint8_t* red_b = take(sizeof(XYZZ<F>) * list_slots);
+
+    const uint32_t* gen_count = nullptr;
+    const uint32_t* gen_idx = nullptr;
+    const uint8_t* ones_sum = nullptr;
+    if (classify) {
+        cudaMemsetAsync(counters, 0, 8, st);
+        classify_kernel<F><<<(n + 255) / 256, 256, 0, st>>>(points, scalars, n, ones_list, gen_list, counters);
+        ZKE_COUNT_LAUNCH(2);
+        // ones: tree reduction with fan-in LIST_FANIN; level sizes are computed on the device from counters[0]
+        uint32_t upper = n;
+        uint32_t lvl_out = (upper + LIST_FANIN - 1) / LIST_FANIN;
+        sum_affine_list_kernel<F><<<(lvl_out + 127) / 128, 128, 0, st>>>(points, ones_list, counters, 0, red_a);
+        uint8_t *src = red_a, *dst = red_b;
+        uint32_t div = 1;
+        upper = lvl_out;
+        while (upper > 1) {
+            lvl_out = (upper + LIST_FANIN - 1) / LIST_FANIN;
+            sum_xyzz_kernel<F><<<(lvl_out + 127) / 128, 128, 0, st>>>(src, counters, 0, div, dst);
+            ZKE_COUNT_LAUNCH(1);
+            uint8_t* t = src; src = dst; dst = t;
+            upper = lvl_out;
+            ++div;
+        }
+        ones_sum = src;   // slot 0 (the point at infinity if the list was empty)
+        gen_count = counters + 1;
+        gen_idx = gen_list;
+    }
+    cudaMemsetAsync(hist, 0, 4 * ((size_t)n_buckets + 1), st);
+    cudaMemsetAsync(cursor, 0, 4 * ((size_t)n_buckets + 1), st);
+    const int grid = 148 * 8;
+    digit_hist_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, hist);
+    scan_kernel<<<1, 1024, 0, st>>>(hist, n_buckets, 0, offsets);
+    digit_scatter_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, offsets, cursor, entries);
+    scan_kernel<<<1, 1024, 0, st>>>(hist, n_buckets, 1, chunk_off);
+    fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, chunk_off, n_buckets, work_bucket);
+    chunk_sum_kernel<F><<<148 * 16, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, partial);
+    group_sum_kernel<F><<<(groups + 127) / 128, 128, 0, st>>>(partial, hist, chunk_off, D.half, groups, group_out);
+    window_reduce_kernel<F><<<D.n_windows, 512, 0, st>>>(group_out, groups_per_window);
+    msm_final_kernel<F><<<1, 32, 0, st>>>(group_out, groups_per_window, D, ones_sum, 1, result);
+    ZKE_COUNT_LAUNCH(9);
+}
+
+template struct MsmPlan<Fq>;
+template struct MsmPlan<Fq2>;
+
+}  // namespace dev
+}  // namespace zke

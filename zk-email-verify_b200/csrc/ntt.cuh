@@ -1,0 +1,23 @@
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace zke {
+namespace dev {
+
+struct NttTables {
+    const uint8_t* tw_fwd;   // [N/2][32] omega^k, Montgomery
+    const uint8_t* tw_inv;   // [N/2][32] omega^-k
+    int log_n;
+};
+
+// In-place inverse transform, natural order in, BIT-REVERSED order out, not scaled by 1/N.  If scale_bitrev is
+// non-null, output position p is multiplied by scale_bitrev[p] (used to fuse the coset shift g^j / N).
+void launch_intt_dif(uint8_t* data, const NttTables& T, const uint8_t* scale_bitrev, cudaStream_t st);
+// In-place forward transform, bit-reversed order in, natural order out.
+void launch_ntt_dit(uint8_t* data, const NttTables& T, cudaStream_t st);
+void launch_hadamard(const uint8_t* a, const uint8_t* b, uint8_t* c, uint32_t n, cudaStream_t st);
+void launch_quotient(const uint8_t* a, const uint8_t* b, const uint8_t* c, uint8_t* d, uint32_t n, cudaStream_t st);
+
+}  // namespace dev
+}  // namespace zke

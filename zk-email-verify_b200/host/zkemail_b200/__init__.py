@@ -8,3 +8,5 @@ from .sha_utils import generate_partial_sha, partial_sha, sha256_pad, sha_hash  
 from .dkim import DKIMVerificationResult, verify_dkim_signature  # noqa: F401
 from .input_generators import (generate_circuit_inputs, generate_email_verifier_inputs,  # noqa: F401
                                generate_email_verifier_inputs_from_dkim_result)
+from .engine import AssertFailed, Context, Zkey, device_count, proof_to_json, verify  # noqa: F401
+from .chunked_zkey import generate_proof, verify_proof, register_circuit, generateProof, verifyProof  # noqa: F401

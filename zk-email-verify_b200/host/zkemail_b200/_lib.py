@@ -55,3 +55,29 @@ zke_version = _sig("zke_version", c_char_p, [])
 
 class ZkeError(RuntimeError):
     pass
+
+# ---- engine (needs a CUDA device) -----------------------------------------------------------------------
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+zke_setup = _sig("zke_setup", c_void_p, [c_void_p, c_u64, c_int, c_char_p, c_size_t])
+zke_zkey_free = _sig("zke_zkey_free", None, [c_void_p])
+zke_zkey_info = _sig("zke_zkey_info", c_int, [c_void_p, ctypes.POINTER(c_u32), ctypes.POINTER(c_u32), ctypes.POINTER(c_u32)])
+zke_zkey_section = _sig("zke_zkey_section", c_i64, [c_void_p, c_int, c_void_p, c_size_t])
+zke_ctx_open = _sig("zke_ctx_open", c_void_p, [c_void_p, c_void_p, c_int, c_u32, c_char_p, c_size_t])
+zke_ctx_close = _sig("zke_ctx_close", None, [c_void_p])
+zke_ctx_stream = _sig("zke_ctx_stream", c_void_p, [c_void_p])
+zke_kernel_launches = _sig("zke_kernel_launches", c_u64, [])
+zke_witness = _sig("zke_witness", c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_char_p, c_size_t])
+zke_load_witness = _sig("zke_load_witness", c_int, [c_void_p, c_void_p, c_size_t, c_char_p, c_size_t])
+zke_prove = _sig("zke_prove", c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_char_p, c_size_t])
+zke_fullprove = _sig("zke_fullprove", c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_char_p, c_size_t])
+zke_verify_json = _sig("zke_verify_json", c_int, [c_char_p, c_char_p, c_char_p, c_char_p, c_size_t])
+zke_zkey_vkey_json = _sig("zke_zkey_vkey_json", c_int, [c_void_p, c_char_p, ctypes.POINTER(c_size_t)])
+zke_proof_to_json = _sig("zke_proof_to_json", c_int, [c_void_p, c_void_p, c_u32, c_char_p, ctypes.POINTER(c_size_t), c_char_p, ctypes.POINTER(c_size_t)])
+zke_pack_inputs_json = _sig("zke_pack_inputs_json", c_int, [c_void_p, c_char_p, c_void_p, c_size_t, c_char_p, c_size_t])
+zke_fullprove_json = _sig("zke_fullprove_json", c_int, [c_void_p, c_void_p, c_char_p, c_char_p, ctypes.POINTER(c_size_t), c_char_p,
+                                                        ctypes.POINTER(c_size_t), c_char_p, c_size_t])
+zke_selftest_fpmul_hint = _sig("zke_selftest_fpmul_hint", c_int, [c_u32, c_u32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p])
+
+(SEC_ALPHA1, SEC_BETA1, SEC_DELTA1, SEC_BETA2, SEC_GAMMA2, SEC_DELTA2) = (101, 102, 103, 104, 105, 106)
+(SEC_IC, SEC_A, SEC_B1, SEC_B2, SEC_C, SEC_H) = (3, 5, 6, 7, 8, 9)

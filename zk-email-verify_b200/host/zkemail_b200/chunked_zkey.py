@@ -1,0 +1,43 @@
+"""Mirror of the prove / verify shim of /root/reference/packages/helpers/src/chunked-zkey.ts:76-105.
+
+The reference resolves `${circuitName}.wasm` / `${circuitName}.zkey` by URL and hands them to snarkjs; here a
+circuit name resolves to a registered (Circuit, Zkey, Context) triple resident on a GPU."""
+from __future__ import annotations
+import json
+from .engine import Context, Zkey, proof_to_json, verify
+from .circuit import Circuit
+
+_REGISTRY: dict[str, tuple] = {}
+
+
+def register_circuit(circuit_name: str, circuit: Circuit, zkey: Zkey, device: int = 0, max_batch: int = 1):
+    """Plays the role of downloadProofFiles (chunked-zkey.ts:59-74): makes the proving artefacts of `circuitName`
+    available to generateProof / verifyProof."""
+    ctx = Context(circuit, zkey, device=device, max_batch=max_batch)
+    _REGISTRY[circuit_name] = (circuit, zkey, ctx, zkey.vkey())
+    return ctx
+
+
+def generate_proof(input: dict, base_url: str, circuit_name: str):
+    """generateProof(input, baseUrl, circuitName) -> {proof, publicSignals}  (chunked-zkey.ts:76-91 ->
+    snarkjs.groth16.fullProve)."""
+    if circuit_name not in _REGISTRY:
+        raise KeyError(f"Error downloading {base_url}{circuit_name}.zkey after 3 retries")   # chunked-zkey.ts:32
+    circuit, _, ctx, _ = _REGISTRY[circuit_name]
+    packed = circuit.pack_inputs(input)
+    proofs, publics, _ = ctx.fullprove(packed, 1)
+    proof, public_signals = proof_to_json(proofs[:256], publics, circuit.info.n_public)
+    return {"proof": proof, "publicSignals": public_signals}
+
+
+def verify_proof(proof: dict, public_signals, base_url: str, circuit_name: str) -> bool:
+    """verifyProof(proof, publicSignals, baseUrl, circuitName) (chunked-zkey.ts:93-105 -> snarkjs.groth16.verify)."""
+    if circuit_name not in _REGISTRY:
+        raise KeyError(f"Error downloading {base_url}{circuit_name}.vkey.json after 3 retries")
+    vkey = _REGISTRY[circuit_name][3]
+    return verify(vkey, public_signals, proof)
+
+
+# camelCase aliases matching the reference's exports
+generateProof = generate_proof
+verifyProof = verify_proof

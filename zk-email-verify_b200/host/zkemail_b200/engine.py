@@ -1,0 +1,143 @@
+"""Proving key and GPU context wrappers over the C ABI (zke_setup / zke_ctx_* / zke_witness / zke_prove)."""
+from __future__ import annotations
+import ctypes
+import json
+from . import _lib as L
+from .circuit import Circuit
+
+
+class AssertFailed(L.ZkeError):
+    """Raised when a witness violates a constraint; the message contains "Assert Failed" - the string the
+    reference's tests match (/root/reference/packages/circuits/tests/email-verifier.test.ts:78)."""
+
+
+def device_count() -> int:
+    return L.zke_device_count()
+
+
+class Zkey:
+    def __init__(self, circuit: Circuit, seed: int = 1, device: int = 0):
+        err = ctypes.create_string_buffer(L.ERRCAP)
+        self._h = L.zke_setup(circuit.handle, seed, device, err, L.ERRCAP)
+        if not self._h:
+            raise L.ZkeError(err.value.decode())
+        self.circuit, self.device = circuit, device
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            L.zke_zkey_free(self._h)
+            self._h = None
+
+    @property
+    def handle(self):
+        return self._h
+
+    def vkey(self) -> dict:
+        """`snarkjs zkey export verificationkey` -> vkey.json object."""
+        n = L.c_size_t(0)
+        L.zke_zkey_vkey_json(self._h, None, ctypes.byref(n))
+        buf = ctypes.create_string_buffer(n.value)
+        n2 = L.c_size_t(n.value)
+        if L.zke_zkey_vkey_json(self._h, buf, ctypes.byref(n2)) != 0:
+            raise L.ZkeError("vkey export failed")
+        return json.loads(buf.value.decode())
+
+    def section(self, sec: int) -> bytes:
+        cnt = L.zke_zkey_section(self._h, sec, None, 0)
+        if cnt < 0:
+            raise L.ZkeError("bad section")
+        size = 128 if sec in (L.SEC_BETA2, L.SEC_GAMMA2, L.SEC_DELTA2, L.SEC_B2) else 64
+        buf = ctypes.create_string_buffer(size * cnt)
+        if L.zke_zkey_section(self._h, sec, buf, len(buf)) < 0:
+            raise L.ZkeError("section read failed")
+        return buf.raw
+
+
+class Context:
+    def __init__(self, circuit: Circuit, zkey: Zkey | None = None, device: int = 0, max_batch: int = 1):
+        err = ctypes.create_string_buffer(L.ERRCAP)
+        self._h = L.zke_ctx_open(circuit.handle, zkey.handle if zkey else None, device, max_batch, err, L.ERRCAP)
+        if not self._h:
+            raise L.ZkeError(err.value.decode())
+        self.circuit, self.zkey, self.device, self.max_batch = circuit, zkey, device, max_batch
+
+    def close(self):
+        if getattr(self, "_h", None):
+            L.zke_ctx_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def handle(self):
+        return self._h
+
+    @property
+    def stream(self) -> int:
+        return L.zke_ctx_stream(self._h) or 0
+
+    def witness(self, packed_inputs: bytes, batch: int, want_witness: bool = True, raise_on_fail: bool = True):
+        """calculateWitness + checkConstraints.  Returns (witness bytes | None, status list)."""
+        m = self.circuit.info.n_vars
+        out = ctypes.create_string_buffer(32 * m * batch) if want_witness else None
+        status = (ctypes.c_int32 * batch)()
+        err = ctypes.create_string_buffer(L.ERRCAP)
+        rc = L.zke_witness(self._h, packed_inputs, batch, out, status, err, L.ERRCAP)
+        if rc < 0:
+            raise L.ZkeError(err.value.decode())
+        if rc > 0 and raise_on_fail:
+            raise AssertFailed(err.value.decode())
+        return (out.raw if out is not None else None), list(status)
+
+    def load_witness(self, wtns: bytes, batch: int):
+        err = ctypes.create_string_buffer(L.ERRCAP)
+        if L.zke_load_witness(self._h, wtns, batch, err, L.ERRCAP) != 0:
+            raise L.ZkeError(err.value.decode())
+
+    def _prove_call(self, fn, head_args, batch, rs, raise_on_fail):
+        npub = self.circuit.info.n_public
+        proofs = ctypes.create_string_buffer(256 * batch)
+        publics = ctypes.create_string_buffer(max(1, 32 * npub * batch))
+        status = (ctypes.c_int32 * batch)()
+        err = ctypes.create_string_buffer(L.ERRCAP)
+        rc = fn(self._h, *head_args, batch, rs, proofs, publics, status, err, L.ERRCAP)
+        if rc < 0:
+            raise L.ZkeError(err.value.decode())
+        if rc > 0 and raise_on_fail:
+            raise AssertFailed(err.value.decode())
+        return proofs.raw, publics.raw[: 32 * npub * batch], list(status)
+
+    def prove(self, batch: int, rs: bytes | None = None, raise_on_fail: bool = True):
+        return self._prove_call(L.zke_prove, (), batch, rs, raise_on_fail)
+
+    def fullprove(self, packed_inputs: bytes, batch: int, rs: bytes | None = None, raise_on_fail: bool = True):
+        npub = self.circuit.info.n_public
+        proofs = ctypes.create_string_buffer(256 * batch)
+        publics = ctypes.create_string_buffer(max(1, 32 * npub * batch))
+        status = (ctypes.c_int32 * batch)()
+        err = ctypes.create_string_buffer(L.ERRCAP)
+        rc = L.zke_fullprove(self._h, packed_inputs, batch, rs, proofs, publics, status, err, L.ERRCAP)
+        if rc < 0:
+            raise L.ZkeError(err.value.decode())
+        if rc > 0 and raise_on_fail:
+            raise AssertFailed(err.value.decode())
+        return proofs.raw, publics.raw[: 32 * npub * batch], list(status)
+
+
+def proof_to_json(proof256: bytes, publics: bytes, n_public: int):
+    """256-byte proof + packed public signals -> (proof.json object, publicSignals list) in snarkjs format."""
+    pl, sl = L.c_size_t(4096), L.c_size_t(80 * max(1, n_public) + 16)
+    pj, sj = ctypes.create_string_buffer(pl.value), ctypes.create_string_buffer(sl.value)
+    if L.zke_proof_to_json(proof256, publics, n_public, pj, ctypes.byref(pl), sj, ctypes.byref(sl)) != 0:
+        raise L.ZkeError("proof_to_json failed")
+    return json.loads(pj.value.decode()), json.loads(sj.value.decode())
+
+
+def verify(vkey: dict, public_signals, proof: dict) -> bool:
+    """snarkjs.groth16.verify(vkey, publicSignals, proof) (/root/reference/packages/helpers/src/chunked-zkey.ts:101)."""
+    err = ctypes.create_string_buffer(L.ERRCAP)
+    rc = L.zke_verify_json(json.dumps(vkey).encode(), json.dumps([str(s) for s in public_signals]).encode(),
+                           json.dumps(proof).encode(), err, L.ERRCAP)
+    if rc < 0:
+        raise L.ZkeError(err.value.decode())
+    return rc == 1
