@@ -82,10 +82,6 @@ std::vector<U256> to_standard(const std::vector<Fr>& v) {
     return out;
 }
 
-template <class F>
-void put_le(uint8_t* dst, const F& x);
-template <> void put_le<Fq>(uint8_t* dst, const Fq& x) { U256 s = x.to_u256(); memcpy(dst, s.v, 32); }
-
 }  // namespace
 
 struct zke_zkey {

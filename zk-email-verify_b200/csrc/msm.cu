@@ -90,9 +90,10 @@ __device__ __forceinline__ void for_each_digit(const Fr& s, const Digits& D, Fn 
     uint32_t carry = 0;
     for (int j = 0; j < D.n_windows; ++j) {
         uint32_t raw = window_bits(s, j * D.c, D.c) + carry;
-        if (raw > D.half) {                      // digit = raw - 2^c  (negative), carry 1
+        if (raw > D.half) {                      // digit = raw - 2^c  (negative or zero), carry 1
             carry = 1;
-            f(j, (1u << D.c) - raw - 1, true);
+            const uint32_t mag = (1u << D.c) - raw;   // raw == 2^c (all-ones window plus carry) gives digit 0
+            if (mag) f(j, mag - 1, true);
         } else {
             carry = 0;
             if (raw) f(j, raw - 1, false);
