@@ -114,8 +114,27 @@ void zke_ctx_close(zke_ctx* x);
 void* zke_ctx_stream(const zke_ctx* x);      /* the cudaStream_t all of the context's work is enqueued on */
 uint64_t zke_kernel_launches(void);          /* kernels launched by this library since it was loaded */
 
+/* Copies a batch of packed inputs into the context's device buffer; a later zke_witness / zke_fullprove call with
+ * inputs == NULL uses them (lets a benchmark start its timed region with the inputs already resident in HBM). */
+int zke_upload_inputs(zke_ctx* x, const uint8_t* inputs, size_t batch, char* err, size_t errcap);
+
+/* Optional per-stage device timing (CUDA events on the context's stream, accumulated over calls). */
+enum {
+    ZKE_STAGE_WITNESS = 0,        /* witness kernel, whole batch                                   */
+    ZKE_STAGE_MATVEC = 1,         /* <A,w>, <B,w>, constraint check, per email                     */
+    ZKE_STAGE_NTT = 2,            /* hadamard + 3 inverse + 3 forward NTTs + quotient, per email   */
+    ZKE_STAGE_MSM_A = 3, ZKE_STAGE_MSM_B1 = 4, ZKE_STAGE_MSM_C = 5,
+    ZKE_STAGE_MSM_H = 6,          /* whole H multi-exponentiation (N full-width scalars)           */
+    ZKE_STAGE_MSM_H_BUCKETS = 7,  /* its bucket-accumulation kernel alone (the dominant kernel)    */
+    ZKE_STAGE_MSM_B2 = 8,
+    ZKE_N_STAGES = 9
+};
+int zke_ctx_profile(zke_ctx* x, int enable);                       /* enabling also clears the accumulators */
+int zke_ctx_profile_get(const zke_ctx* x, double* ms_out, uint64_t* count_out);  /* arrays of ZKE_N_STAGES */
+
 /* calculateWitness + checkConstraints for a batch (circom_tester verbs; witness step of fullProve).
- * inputs: [batch][n_inputs][32] in witness order (see zke_circuit_input_offset).  wtns_out (optional):
+ * inputs: [batch][n_inputs][32] in witness order (see zke_circuit_input_offset), or NULL to use the inputs made
+ * resident by zke_upload_inputs.  wtns_out (optional):
  * [batch][n_vars][32], the `.wtns` payload.  status (optional): per email, -1 = satisfied, else the index of
  * the first violated constraint.  Returns the number of failing emails (message: "Assert Failed: ..."). */
 int zke_witness(zke_ctx* x, const uint8_t* inputs, size_t batch, uint8_t* wtns_out, int32_t* status,
@@ -151,6 +170,9 @@ int zke_fullprove_json(zke_ctx* x, const zke_circuit* c, const char* input_json,
                        char* public_json, size_t* public_len, char* err, size_t errcap);
 /* Diagnostic: the FpMul big-integer hint evaluated on the host with the same code the witness kernel runs
  * (a, b, p: k limbs of 32 bytes LE; q, r out likewise). */
+/* Diagnostic: the toxic waste (tau, alpha, beta, gamma, delta; 5 x 32 bytes LE) zke_setup derives from `seed` -
+ * lets a test rebuild the same key independently.  It exists precisely because the setup is a toy. */
+int zke_setup_toxic(uint64_t seed, uint8_t* out160);
 int zke_selftest_fpmul_hint(uint32_t n, uint32_t k, const uint8_t* a, const uint8_t* b, const uint8_t* p, uint8_t* q, uint8_t* r);
 
 /* Library / device introspection.  zke_device_count() returns 0 when no CUDA device is usable;

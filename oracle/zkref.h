@@ -23,4 +23,23 @@ int zkref_witness(const zkref_circuit* C, const uint8_t* inputs, uint8_t* w);
 /* checkConstraints: index of the first violated R1CS row, or -1 */
 int64_t zkref_check_r1cs(const zkref_circuit* C, const uint8_t* w);
 
+
+/* Proving key as flat standard-form affine point arrays (the images returned by the product's zke_zkey_section). */
+typedef struct {
+    uint32_t n_vars, n_public, log_n, pad_;
+    const uint8_t *alpha1, *beta1, *delta1;   /* G1, 64 bytes each */
+    const uint8_t *beta2, *delta2;            /* G2, 128 bytes each */
+    const uint8_t *A, *B1, *C, *H;            /* G1 arrays: n_vars, n_vars, n_vars, 2^log_n points */
+    const uint8_t* B2;                        /* G2 array: n_vars points */
+} zkref_zkey;
+
+/* snarkjs groth16.prove: witness w [n_vars][32], blinding r, s (32 bytes LE each) -> proof
+ * [A.x A.y B.x.c0 B.x.c1 B.y.c0 B.y.c1 C.x C.y] x 32 bytes LE standard form. */
+int zkref_groth16_prove(const zkref_circuit* C, const zkref_zkey* K, const uint8_t* w, const uint8_t* r32, const uint8_t* s32,
+                        int threads, uint8_t* proof256);
+/* Toy setup for SMALL circuits from explicit toxic waste (tau, alpha, beta, gamma, delta: 5 x 32 bytes). */
+int zkref_groth16_setup(const zkref_circuit* C, unsigned log_n, uint32_t n_public, const uint8_t* toxic,
+                        uint8_t* A, uint8_t* B1, uint8_t* B2, uint8_t* Cs, uint8_t* H, uint8_t* IC,
+                        uint8_t* alpha1, uint8_t* beta1, uint8_t* delta1, uint8_t* beta2, uint8_t* gamma2, uint8_t* delta2);
+
 #endif

@@ -3,6 +3,7 @@
 #include "engine.hpp"
 #include "gadgets.hpp"
 #include "bigdiv.hpp"
+#include "setup_host.hpp"
 #include <cstdio>
 #include <cstring>
 
@@ -252,6 +253,14 @@ const char* zke_circuit_scope_name(const zke_circuit* c, uint32_t i) {
 int zke_selftest_fpmul_hint(uint32_t n, uint32_t k, const uint8_t* a, const uint8_t* b, const uint8_t* p, uint8_t* q, uint8_t* r) {
     if (k > 32) return 1;
     return fpmul_hint_words(n, k, (const uint32_t*)a, (const uint32_t*)b, (const uint32_t*)p, (uint32_t*)q, (uint32_t*)r);
+}
+
+int zke_setup_toxic(uint64_t seed, uint8_t* out160) {
+    if (!out160) return -1;
+    Fr t[5];
+    derive_toxic(seed, t);
+    for (int i = 0; i < 5; ++i) { U256 x = t[i].to_u256(); memcpy(out160 + 32 * i, x.v, 32); }
+    return 0;
 }
 
 const char* zke_version(void) { return "zkemail_b200 0.1 (sm_100a)"; }

@@ -111,7 +111,30 @@ struct zke_ctx {
     size_t stride = 0;           // witness elements per email (n_vars + n_temps)
     DevBuf w_all, inputs, va, vb, vc, vd, msm_ws, results, first_bad;
     uint32_t loaded = 0;         // number of witnesses currently resident
+    uint32_t inputs_resident = 0; // batch size of the inputs currently in `inputs`
     std::vector<uint32_t> bad_host;
+    // optional stage profiling (CUDA events on `stream`)
+    bool profile = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int stage; size_t e0, e1; };
+    std::vector<Span> spans;
+    double stage_ms[ZKE_N_STAGES] = {0};
+    uint64_t stage_count[ZKE_N_STAGES] = {0};
+    cudaEvent_t ev(size_t* idx) {
+        if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+        *idx = ev_used;
+        return ev_pool[ev_used++];
+    }
+    size_t mark() { size_t i; cudaEventRecord(ev(&i), stream); return i; }
+    void collect() {   // call after the stream has been synchronised
+        for (auto& s : spans) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ev_pool[s.e0], ev_pool[s.e1]) == cudaSuccess) { stage_ms[s.stage] += ms; stage_count[s.stage]++; }
+        }
+        spans.clear();
+        ev_used = 0;
+    }
 };
 
 // ------------------------------------------------------------------------------------------------ setup
@@ -296,8 +319,16 @@ static void do_witness(zke_ctx* x, const uint8_t* inputs, size_t batch) {
     const Circuit& c = x->circuit->c;
     if (batch == 0 || batch > x->max_batch) throw std::runtime_error("batch exceeds the context's max_batch");
     CUDA_OK(cudaSetDevice(x->device));
-    if (c.n_inputs()) CUDA_OK(cudaMemcpyAsync(x->inputs.p, inputs, (size_t)c.n_inputs() * 32 * batch, cudaMemcpyHostToDevice, x->stream));
+    if (inputs) {
+        if (c.n_inputs()) CUDA_OK(cudaMemcpyAsync(x->inputs.p, inputs, (size_t)c.n_inputs() * 32 * batch, cudaMemcpyHostToDevice, x->stream));
+        x->inputs_resident = (uint32_t)batch;
+    } else if (x->inputs_resident < batch) {
+        throw std::runtime_error("inputs == NULL but no (or too few) inputs are resident: call zke_upload_inputs first");
+    }
+    size_t p0 = 0;
+    if (x->profile) p0 = x->mark();
     dev::launch_witness(x->prog, x->w_all.p, x->stride, x->inputs.p, (uint32_t)batch, x->stream);
+    if (x->profile) x->spans.push_back({ZKE_STAGE_WITNESS, p0, x->mark()});
     x->loaded = (uint32_t)batch;
 }
 
@@ -315,6 +346,7 @@ static int do_check(zke_ctx* x, size_t batch, int32_t* status, std::string& msg)
     }
     CUDA_OK(cudaMemcpyAsync(x->bad_host.data(), x->first_bad.p, 4 * batch, cudaMemcpyDeviceToHost, x->stream));
     CUDA_OK(cudaStreamSynchronize(x->stream));
+    if (x->profile) x->collect();
     int bad = 0;
     for (size_t e = 0; e < batch; ++e) {
         int32_t s = x->bad_host[e] == 0xffffffffu ? -1 : (int32_t)x->bad_host[e];
@@ -345,7 +377,11 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
     for (size_t e = 0; e < batch; ++e) {
         const uint8_t* w = x->w_all.p + 32 * x->stride * e;
         uint8_t* res = x->results.p + ZKE_RESULT_STRIDE * e;
+        const bool prof = x->profile;
+        size_t t0 = 0, t1 = 0;
+        if (prof) t0 = x->mark();
         dev::launch_build_ab(x->r1cs, w, x->va.p, x->vb.p, N, (uint32_t*)x->first_bad.p + e, st);
+        if (prof) { t1 = x->mark(); x->spans.push_back({ZKE_STAGE_MATVEC, t0, t1}); t0 = t1; }
         dev::launch_hadamard(x->va.p, x->vb.p, x->vc.p, N, st);
         dev::launch_intt_dif(x->va.p, x->ntt, x->coset_scale.p, st);
         dev::launch_intt_dif(x->vb.p, x->ntt, x->coset_scale.p, st);
@@ -354,11 +390,25 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
         dev::launch_ntt_dit(x->vb.p, x->ntt, st);
         dev::launch_ntt_dit(x->vc.p, x->ntt, st);
         dev::launch_quotient(x->va.p, x->vb.p, x->vc.p, x->vd.p, N, st);
+        if (prof) { t1 = x->mark(); x->spans.push_back({ZKE_STAGE_NTT, t0, t1}); t0 = t1; }
         dev::MsmPlan<dev::Fq>::run(zk->A.p, w, m, ZKE_MSM_C_WITNESS, true, x->msm_ws.p, res + 0, st);
+        if (prof) { t1 = x->mark(); x->spans.push_back({ZKE_STAGE_MSM_A, t0, t1}); t0 = t1; }
         dev::MsmPlan<dev::Fq>::run(zk->B1.p, w, m, ZKE_MSM_C_WITNESS, true, x->msm_ws.p, res + 128, st);
+        if (prof) { t1 = x->mark(); x->spans.push_back({ZKE_STAGE_MSM_B1, t0, t1}); t0 = t1; }
         dev::MsmPlan<dev::Fq>::run(zk->C.p, w, m, ZKE_MSM_C_WITNESS, true, x->msm_ws.p, res + 256, st);
-        dev::MsmPlan<dev::Fq>::run(zk->H.p, x->vd.p, N, ZKE_MSM_C_H, false, x->msm_ws.p, res + 384, st);
+        if (prof) { t1 = x->mark(); x->spans.push_back({ZKE_STAGE_MSM_C, t0, t1}); t0 = t1; }
+        if (prof) {
+            size_t i0, i1;
+            cudaEvent_t evs[2] = {x->ev(&i0), nullptr};
+            evs[1] = x->ev(&i1);
+            dev::MsmPlan<dev::Fq>::run(zk->H.p, x->vd.p, N, ZKE_MSM_C_H, false, x->msm_ws.p, res + 384, st, evs);
+            x->spans.push_back({ZKE_STAGE_MSM_H_BUCKETS, i0, i1});
+            t1 = x->mark(); x->spans.push_back({ZKE_STAGE_MSM_H, t0, t1}); t0 = t1;
+        } else {
+            dev::MsmPlan<dev::Fq>::run(zk->H.p, x->vd.p, N, ZKE_MSM_C_H, false, x->msm_ws.p, res + 384, st);
+        }
         dev::MsmPlan<dev::Fq2>::run(zk->B2.p, w, m, ZKE_MSM_C_WITNESS, true, x->msm_ws.p, res + 512, st);
+        if (prof) { t1 = x->mark(); x->spans.push_back({ZKE_STAGE_MSM_B2, t0, t1}); t0 = t1; }
     }
     std::vector<uint8_t> res_host(ZKE_RESULT_STRIDE * batch);
     std::vector<uint8_t> pub_host((size_t)std::max(1u, l) * 32 * batch);
@@ -366,6 +416,7 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
     CUDA_OK(cudaMemcpyAsync(x->bad_host.data(), x->first_bad.p, 4 * batch, cudaMemcpyDeviceToHost, st));
     if (l) CUDA_OK(cudaMemcpy2DAsync(pub_host.data(), (size_t)l * 32, x->w_all.p + 32, x->stride * 32, (size_t)l * 32, batch, cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
+    if (x->profile) x->collect();
 
     int bad = 0;
     const G1JacH alpha1 = G1JacH::from_affine(zk->alpha1), beta1 = G1JacH::from_affine(zk->beta1), delta1 = G1JacH::from_affine(zk->delta1);
@@ -486,8 +537,33 @@ zke_ctx* zke_ctx_open(const zke_circuit* c, const zke_zkey* zkey, int device, ui
 void zke_ctx_close(zke_ctx* x) {
     if (!x) return;
     cudaSetDevice(x->device);
+    for (auto e : x->ev_pool) cudaEventDestroy(e);
     if (x->stream) cudaStreamDestroy(x->stream);
     delete x;
+}
+
+int zke_upload_inputs(zke_ctx* x, const uint8_t* inputs, size_t batch, char* err, size_t errcap) {
+    try {
+        if (!x || !inputs) throw std::runtime_error("null argument");
+        if (batch == 0 || batch > x->max_batch) throw std::runtime_error("batch exceeds the context's max_batch");
+        CUDA_OK(cudaSetDevice(x->device));
+        const size_t n = x->circuit->c.n_inputs();
+        if (n) CUDA_OK(cudaMemcpy(x->inputs.p, inputs, n * 32 * batch, cudaMemcpyHostToDevice));
+        x->inputs_resident = (uint32_t)batch;
+        return 0;
+    } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+
+int zke_ctx_profile(zke_ctx* x, int enable) {
+    if (!x) return -1;
+    x->profile = enable != 0;
+    for (int i = 0; i < ZKE_N_STAGES; ++i) { x->stage_ms[i] = 0; x->stage_count[i] = 0; }
+    return 0;
+}
+int zke_ctx_profile_get(const zke_ctx* x, double* ms_out, uint64_t* count_out) {
+    if (!x) return -1;
+    for (int i = 0; i < ZKE_N_STAGES; ++i) { if (ms_out) ms_out[i] = x->stage_ms[i]; if (count_out) count_out[i] = x->stage_count[i]; }
+    return ZKE_N_STAGES;
 }
 void* zke_ctx_stream(const zke_ctx* x) { return x ? (void*)x->stream : nullptr; }
 uint64_t zke_kernel_launches(void) { return dev::g_kernel_launches; }

@@ -269,7 +269,7 @@ size_t MsmPlan<F>::workspace_bytes(uint32_t n, int c) {
 
 template <class F>
 void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, int c, bool classify, uint8_t* ws,
-                     uint8_t* result, cudaStream_t st) {
+                     uint8_t* result, cudaStream_t st, cudaEvent_t* ev) {
     Digits D;
     D.c = c;
     D.n_windows = (255 + c - 1) / c;
@@ -330,7 +330,9 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     digit_scatter_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, offsets, cursor, entries);
     scan_kernel<<<1, 1024, 0, st>>>(hist, n_buckets, 1, chunk_off);
     fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, chunk_off, n_buckets, work_bucket);
+    if (ev) cudaEventRecord(ev[0], st);
     chunk_sum_kernel<F><<<148 * 16, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, partial);
+    if (ev) cudaEventRecord(ev[1], st);
     group_sum_kernel<F><<<(groups + 127) / 128, 128, 0, st>>>(partial, hist, chunk_off, D.half, groups, group_out);
     window_reduce_kernel<F><<<D.n_windows, 512, 0, st>>>(group_out, groups_per_window);
     msm_final_kernel<F><<<1, 32, 0, st>>>(group_out, groups_per_window, D, ones_sum, 1, result);

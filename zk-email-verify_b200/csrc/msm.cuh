@@ -14,8 +14,9 @@ namespace dev {
 template <class F>
 struct MsmPlan {
     static size_t workspace_bytes(uint32_t n, int c);
+    // ev (optional): two events recorded immediately before / after the bucket-accumulation kernel (profiling)
     static void run(const uint8_t* points, const uint8_t* scalars, uint32_t n, int c, bool classify, uint8_t* workspace,
-                    uint8_t* result, cudaStream_t st);
+                    uint8_t* result, cudaStream_t st, cudaEvent_t* ev = nullptr);
 };
 
 }  // namespace dev

@@ -28,6 +28,8 @@ static Fr fr_from_seed(uint64_t seed, uint64_t stream) {
     return Fr::from_u256(v);
 }
 
+void derive_toxic(uint64_t seed, Fr out[5]) { for (int i = 0; i < 5; ++i) out[i] = fr_from_seed(seed, (uint64_t)i + 1); }
+
 // out[i] = numer * omega^i / (x - omega^i) for i in [0, N)
 static void lagrange_like(const Fr& x, const Fr& numer, unsigned log_n, std::vector<Fr>& out) {
     const size_t N = (size_t)1 << log_n;
@@ -55,8 +57,9 @@ SetupScalars compute_setup_scalars(const Circuit& c, uint64_t seed) {
     S.log_n = c.domain_log2();
     const size_t N = (size_t)1 << S.log_n;
     const uint32_t m = c.n_vars, l = c.n_public();
-    S.tau = fr_from_seed(seed, 1); S.alpha = fr_from_seed(seed, 2); S.beta = fr_from_seed(seed, 3);
-    S.gamma = fr_from_seed(seed, 4); S.delta = fr_from_seed(seed, 5);
+    Fr tox[5];
+    derive_toxic(seed, tox);
+    S.tau = tox[0]; S.alpha = tox[1]; S.beta = tox[2]; S.gamma = tox[3]; S.delta = tox[4];
 
     U256 eN = {{(uint64_t)N, 0, 0, 0}};
     const Fr tauN = S.tau.pow(eN);

@@ -14,5 +14,7 @@ struct SetupScalars {
     std::vector<Fr> h;    // N scalars of the H points
 };
 SetupScalars compute_setup_scalars(const Circuit& c, uint64_t seed);
+// tau, alpha, beta, gamma, delta derived from the seed (the KNOWN toxic waste of the toy setup)
+void derive_toxic(uint64_t seed, Fr out[5]);
 
 }  // namespace zke

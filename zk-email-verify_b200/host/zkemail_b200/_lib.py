@@ -77,6 +77,11 @@ zke_proof_to_json = _sig("zke_proof_to_json", c_int, [c_void_p, c_void_p, c_u32,
 zke_pack_inputs_json = _sig("zke_pack_inputs_json", c_int, [c_void_p, c_char_p, c_void_p, c_size_t, c_char_p, c_size_t])
 zke_fullprove_json = _sig("zke_fullprove_json", c_int, [c_void_p, c_void_p, c_char_p, c_char_p, ctypes.POINTER(c_size_t), c_char_p,
                                                         ctypes.POINTER(c_size_t), c_char_p, c_size_t])
+zke_upload_inputs = _sig("zke_upload_inputs", c_int, [c_void_p, c_void_p, c_size_t, c_char_p, c_size_t])
+zke_ctx_profile = _sig("zke_ctx_profile", c_int, [c_void_p, c_int])
+zke_ctx_profile_get = _sig("zke_ctx_profile_get", c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_u64)])
+STAGES = ("witness", "matvec", "ntt", "msm_a", "msm_b1", "msm_c", "msm_h", "msm_h_buckets", "msm_b2")
+zke_setup_toxic = _sig("zke_setup_toxic", c_int, [c_u64, c_void_p])
 zke_selftest_fpmul_hint = _sig("zke_selftest_fpmul_hint", c_int, [c_u32, c_u32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p])
 
 (SEC_ALPHA1, SEC_BETA1, SEC_DELTA1, SEC_BETA2, SEC_GAMMA2, SEC_DELTA2) = (101, 102, 103, 104, 105, 106)

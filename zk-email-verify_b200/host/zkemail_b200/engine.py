@@ -76,7 +76,21 @@ class Context:
     def stream(self) -> int:
         return L.zke_ctx_stream(self._h) or 0
 
-    def witness(self, packed_inputs: bytes, batch: int, want_witness: bool = True, raise_on_fail: bool = True):
+    def upload_inputs(self, packed_inputs, batch: int):
+        err = ctypes.create_string_buffer(L.ERRCAP)
+        if L.zke_upload_inputs(self._h, packed_inputs, batch, err, L.ERRCAP) != 0:
+            raise L.ZkeError(err.value.decode())
+
+    def profile(self, enable: bool = True):
+        L.zke_ctx_profile(self._h, 1 if enable else 0)
+
+    def profile_get(self) -> dict:
+        n = len(L.STAGES)
+        ms, cnt = (ctypes.c_double * n)(), (L.c_u64 * n)()
+        L.zke_ctx_profile_get(self._h, ms, cnt)
+        return {name: {"ms": ms[i], "count": cnt[i]} for i, name in enumerate(L.STAGES)}
+
+    def witness(self, packed_inputs, batch: int, want_witness: bool = True, raise_on_fail: bool = True):
         """calculateWitness + checkConstraints.  Returns (witness bytes | None, status list)."""
         m = self.circuit.info.n_vars
         out = ctypes.create_string_buffer(32 * m * batch) if want_witness else None
@@ -110,7 +124,7 @@ class Context:
     def prove(self, batch: int, rs: bytes | None = None, raise_on_fail: bool = True):
         return self._prove_call(L.zke_prove, (), batch, rs, raise_on_fail)
 
-    def fullprove(self, packed_inputs: bytes, batch: int, rs: bytes | None = None, raise_on_fail: bool = True):
+    def fullprove(self, packed_inputs, batch: int, rs: bytes | None = None, raise_on_fail: bool = True):
         npub = self.circuit.info.n_public
         proofs = ctypes.create_string_buffer(256 * batch)
         publics = ctypes.create_string_buffer(max(1, 32 * npub * batch))
