@@ -104,12 +104,36 @@ G2AffineH g2_generator();
 bool g1_on_curve(const G1AffineH& p);
 bool g2_on_curve(const G2AffineH& p);
 
-// XYZZ (device accumulator image: x, y, zz, zzz) -> affine
+// Host mirror of the device accumulator (extended Jacobian, x = X/ZZ, y = Y/ZZZ); same memory image.
 template <class F>
-AffineH<F> xyzz_to_affine(const F& x, const F& y, const F& zz, const F& zzz) {
-    if (zz.is_zero()) return AffineH<F>::inf();
-    return AffineH<F>{x * zz.inv(), y * zzz.inv()};
-}
+struct XyzzH {
+    F x, y, zz, zzz;
+    static XyzzH inf() { return XyzzH{F::zero(), F::zero(), F::zero(), F::zero()}; }
+    bool is_inf() const { return zz.is_zero(); }
+    void dbl() {
+        if (is_inf()) return;
+        F U = y + y, V = U.sqr(), W = U * V, S = x * V;
+        F X2 = x.sqr(), M = X2 + X2 + X2;
+        F X3 = M.sqr() - S - S;
+        F Y3 = M * (S - X3) - W * y;
+        zz = V * zz; zzz = W * zzz; x = X3; y = Y3;
+    }
+    void add(const XyzzH& o) {
+        if (o.is_inf()) return;
+        if (is_inf()) { *this = o; return; }
+        F U1 = x * o.zz, U2 = o.x * zz, S1 = y * o.zzz, S2 = o.y * zzz;
+        F P = U2 - U1, R = S2 - S1;
+        if (P.is_zero()) { if (R.is_zero()) { dbl(); return; } *this = inf(); return; }
+        F PP = P.sqr(), PPP = P * PP, Q = U1 * PP;
+        F X3 = R.sqr() - PPP - Q - Q;
+        F Y3 = R * (Q - X3) - S1 * PPP;
+        zz = zz * o.zz * PP; zzz = zzz * o.zzz * PPP; x = X3; y = Y3;
+    }
+    AffineH<F> to_affine() const {
+        if (is_inf()) return AffineH<F>::inf();
+        return AffineH<F>{x * zz.inv(), y * zzz.inv()};
+    }
+};
 
 // Groth16 verification (optimal ate pairing over the Fq2-Fq6-Fq12 tower); see pairing_host.cpp.
 struct VerifyingKey {

@@ -109,7 +109,17 @@ struct zke_ctx {
     dev::NttTables ntt;
     // work buffers
     size_t stride = 0;           // witness elements per email (n_vars + n_temps)
-    DevBuf w_all, inputs, va, vb, vc, vd, msm_ws, results, first_bad;
+    DevBuf w_all, inputs, results, first_bad;
+    // proving lanes: emails are dealt round-robin to `n_lanes` streams, each with its own NTT vectors and MSM
+    // workspace, so that the latency-bound tails of one email's kernels overlap the saturating kernels of another
+    struct Lane { cudaStream_t st = nullptr; DevBuf va, vb, vc, vd, msm_ws; };
+    Lane lanes[ZKE_MAX_LANES];
+    int n_lanes = 1, lanes_alloc = 0;
+    uint8_t* results_host = nullptr;      // pinned, [max_batch][ZKE_RESULT_STRIDE]
+    uint8_t* publics_host = nullptr;      // pinned, [max_batch][n_public][32]
+    std::vector<cudaEvent_t> done;        // per email
+    cudaEvent_t witness_done = nullptr;
+    dev::MsmConfig cfg_w, cfg_h;
     uint32_t loaded = 0;         // number of witnesses currently resident
     uint32_t inputs_resident = 0; // batch size of the inputs currently in `inputs`
     std::vector<uint32_t> bad_host;
@@ -126,7 +136,8 @@ struct zke_ctx {
         *idx = ev_used;
         return ev_pool[ev_used++];
     }
-    size_t mark() { size_t i; cudaEventRecord(ev(&i), stream); return i; }
+    size_t mark(cudaStream_t st) { size_t i; cudaEventRecord(ev(&i), st); return i; }
+    size_t mark() { return mark(stream); }
     void collect() {   // call after the stream has been synchronised
         for (auto& s : spans) {
             float ms = 0;
@@ -297,12 +308,27 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         if (N == 1) { fw[0] = Fr::one(); iv[0] = Fr::one(); }
         x->tw_fwd.upload(fw); x->tw_inv.upload(iv); x->coset_scale.upload(cs);
         x->ntt.tw_fwd = x->tw_fwd.p; x->ntt.tw_inv = x->tw_inv.p; x->ntt.log_n = (int)log_n;
-        x->va.alloc(N * 32); x->vb.alloc(N * 32); x->vc.alloc(N * 32); x->vd.alloc(N * 32);
-        size_t ws = std::max(dev::MsmPlan<dev::Fq>::workspace_bytes(c.n_vars, ZKE_MSM_C_WITNESS),
-                             dev::MsmPlan<dev::Fq>::workspace_bytes((uint32_t)N, ZKE_MSM_C_H));
-        ws = std::max(ws, dev::MsmPlan<dev::Fq2>::workspace_bytes(c.n_vars, ZKE_MSM_C_WITNESS));
-        x->msm_ws.alloc(ws);
+        x->cfg_w = dev::msm_config_witness();
+        x->cfg_h = dev::msm_config_full((uint32_t)N);
+        size_t ws = std::max(dev::MsmPlan<dev::Fq>::workspace_bytes(c.n_vars, x->cfg_w),
+                             dev::MsmPlan<dev::Fq>::workspace_bytes((uint32_t)N, x->cfg_h));
+        ws = std::max(ws, dev::MsmPlan<dev::Fq2>::workspace_bytes(c.n_vars, x->cfg_w));
+        int want = 4;
+        if (const char* e = getenv("ZKE_LANES")) want = atoi(e);
+        want = std::max(1, std::min(ZKE_MAX_LANES, std::min<int>(want, (int)max_batch)));
+        for (int i = 0; i < want; ++i) {
+            zke_ctx::Lane& L = x->lanes[i];
+            CUDA_OK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+            L.va.alloc(N * 32); L.vb.alloc(N * 32); L.vc.alloc(N * 32); L.vd.alloc(N * 32);
+            L.msm_ws.alloc(ws);
+        }
+        x->lanes_alloc = x->n_lanes = want;
         x->results.alloc((size_t)max_batch * ZKE_RESULT_STRIDE);
+        CUDA_OK(cudaHostAlloc((void**)&x->results_host, (size_t)max_batch * ZKE_RESULT_STRIDE, cudaHostAllocDefault));
+        CUDA_OK(cudaHostAlloc((void**)&x->publics_host, (size_t)max_batch * std::max(1u, c.n_public()) * 32, cudaHostAllocDefault));
+        x->done.resize(max_batch);
+        for (auto& e : x->done) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&x->witness_done, cudaEventDisableTiming));
     }
     CUDA_OK(cudaDeviceSynchronize());
     return x.release();
@@ -338,7 +364,7 @@ static int do_check(zke_ctx* x, size_t batch, int32_t* status, std::string& msg)
     const uint32_t rows = c.n_constraints + c.n_public() + 1;
     DevBuf ta, tb;
     uint8_t *pa, *pb;
-    if (x->va.p && x->va.bytes >= (size_t)rows * 32) { pa = x->va.p; pb = x->vb.p; }
+    if (x->lanes[0].va.p && x->lanes[0].va.bytes >= (size_t)rows * 32) { pa = x->lanes[0].va.p; pb = x->lanes[0].vb.p; }
     else { ta.alloc((size_t)rows * 32); tb.alloc((size_t)rows * 32); pa = ta.p; pb = tb.p; }
     CUDA_OK(cudaMemsetAsync(x->first_bad.p, 0xff, 4 * batch, x->stream));
     for (size_t e = 0; e < batch; ++e) {
@@ -356,14 +382,21 @@ static int do_check(zke_ctx* x, size_t batch, int32_t* status, std::string& msg)
     return bad;
 }
 
-template <class F>
-static void read_affine(const uint8_t* xyzz, AffineH<F>& out) {
-    F v[4];
-    memcpy(v, xyzz, sizeof v);
-    out = xyzz_to_affine<F>(v[0], v[1], v[2], v[3]);
-}
-
 static void write_fq(uint8_t* dst, const Fq& x) { U256 s = x.to_u256(); memcpy(dst, s.v, 32); }
+
+// Serial tail of one MSM on the host: sum of the unit-scalar partials + Horner over the window sums.
+template <class F>
+static AffineH<F> finish_msm(const uint8_t* block, const dev::MsmConfig& cfg) {
+    const XyzzH<F>* slots = reinterpret_cast<const XyzzH<F>*>(block);
+    const int n_windows = (255 + cfg.c - 1) / cfg.c;
+    XyzzH<F> acc = XyzzH<F>::inf();
+    for (int j = n_windows - 1; j >= 0; --j) {
+        if (!acc.is_inf()) for (int k = 0; k < cfg.c; ++k) acc.dbl();
+        acc.add(slots[dev::MSM_ONES_SLOTS + j]);
+    }
+    if (cfg.classify) for (int i = 0; i < dev::MSM_ONES_SLOTS; ++i) acc.add(slots[i]);
+    return acc.to_affine();
+}
 
 static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs_out, uint8_t* publics_out, int32_t* status, std::string& msg) {
     const Circuit& c = x->circuit->c;
@@ -372,57 +405,64 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
     if (batch == 0 || batch > x->loaded) throw std::runtime_error("no witness loaded for this batch (call zke_witness first)");
     CUDA_OK(cudaSetDevice(x->device));
     const uint32_t N = 1u << zk->log_n, m = c.n_vars, l = c.n_public();
-    cudaStream_t st = x->stream;
-    CUDA_OK(cudaMemsetAsync(x->first_bad.p, 0xff, 4 * batch, st));
+    const bool prof = x->profile;
+    const int n_lanes = prof ? 1 : x->n_lanes;     // stage timing is only meaningful without overlap
+    // the witnesses were produced on the main stream; the lanes start after it (and after the public signals copy)
+    if (l) CUDA_OK(cudaMemcpy2DAsync(x->publics_host, (size_t)l * 32, x->w_all.p + 32, x->stride * 32, (size_t)l * 32, batch, cudaMemcpyDeviceToHost, x->stream));
+    CUDA_OK(cudaEventRecord(x->witness_done, x->stream));
+    for (int i = 0; i < n_lanes; ++i) CUDA_OK(cudaStreamWaitEvent(x->lanes[i].st, x->witness_done, 0));
     for (size_t e = 0; e < batch; ++e) {
+        zke_ctx::Lane& L = x->lanes[e % n_lanes];
+        cudaStream_t st = L.st;
         const uint8_t* w = x->w_all.p + 32 * x->stride * e;
-        uint8_t* res = x->results.p + ZKE_RESULT_STRIDE * e;
-        const bool prof = x->profile;
+        uint8_t* res = x->results.p + (size_t)ZKE_RESULT_STRIDE * e;
+        uint32_t* flag = (uint32_t*)(res + ZKE_RES_FLAG_OFF);
         size_t t0 = 0, t1 = 0;
-        if (prof) t0 = x->mark();
-        dev::launch_build_ab(x->r1cs, w, x->va.p, x->vb.p, N, (uint32_t*)x->first_bad.p + e, st);
-        if (prof) { t1 = x->mark(); x->spans.push_back({ZKE_STAGE_MATVEC, t0, t1}); t0 = t1; }
-        dev::launch_hadamard(x->va.p, x->vb.p, x->vc.p, N, st);
-        dev::launch_intt_dif(x->va.p, x->ntt, x->coset_scale.p, st);
-        dev::launch_intt_dif(x->vb.p, x->ntt, x->coset_scale.p, st);
-        dev::launch_intt_dif(x->vc.p, x->ntt, x->coset_scale.p, st);
-        dev::launch_ntt_dit(x->va.p, x->ntt, st);
-        dev::launch_ntt_dit(x->vb.p, x->ntt, st);
-        dev::launch_ntt_dit(x->vc.p, x->ntt, st);
-        dev::launch_quotient(x->va.p, x->vb.p, x->vc.p, x->vd.p, N, st);
-        if (prof) { t1 = x->mark(); x->spans.push_back({ZKE_STAGE_NTT, t0, t1}); t0 = t1; }
-        dev::MsmPlan<dev::Fq>::run(zk->A.p, w, m, ZKE_MSM_C_WITNESS, true, x->msm_ws.p, res + 0, st);
-        if (prof) { t1 = x->mark(); x->spans.push_back({ZKE_STAGE_MSM_A, t0, t1}); t0 = t1; }
-        dev::MsmPlan<dev::Fq>::run(zk->B1.p, w, m, ZKE_MSM_C_WITNESS, true, x->msm_ws.p, res + 128, st);
-        if (prof) { t1 = x->mark(); x->spans.push_back({ZKE_STAGE_MSM_B1, t0, t1}); t0 = t1; }
-        dev::MsmPlan<dev::Fq>::run(zk->C.p, w, m, ZKE_MSM_C_WITNESS, true, x->msm_ws.p, res + 256, st);
-        if (prof) { t1 = x->mark(); x->spans.push_back({ZKE_STAGE_MSM_C, t0, t1}); t0 = t1; }
+        CUDA_OK(cudaMemsetAsync(flag, 0xff, 4, st));
+        if (prof) t0 = x->mark(st);
+        dev::launch_build_ab(x->r1cs, w, L.va.p, L.vb.p, N, flag, st);
+        if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MATVEC, t0, t1}); t0 = t1; }
+        dev::launch_hadamard(L.va.p, L.vb.p, L.vc.p, N, st);
+        dev::launch_intt_dif(L.va.p, x->ntt, x->coset_scale.p, st);
+        dev::launch_intt_dif(L.vb.p, x->ntt, x->coset_scale.p, st);
+        dev::launch_intt_dif(L.vc.p, x->ntt, x->coset_scale.p, st);
+        dev::launch_ntt_dit(L.va.p, x->ntt, st);
+        dev::launch_ntt_dit(L.vb.p, x->ntt, st);
+        dev::launch_ntt_dit(L.vc.p, x->ntt, st);
+        dev::launch_quotient(L.va.p, L.vb.p, L.vc.p, L.vd.p, N, st);
+        if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_NTT, t0, t1}); t0 = t1; }
+        dev::MsmPlan<dev::Fq>::run(zk->A.p, w, m, x->cfg_w, L.msm_ws.p, res + 0 * ZKE_RES_G1_BLOCK, st);
+        if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MSM_A, t0, t1}); t0 = t1; }
+        dev::MsmPlan<dev::Fq>::run(zk->B1.p, w, m, x->cfg_w, L.msm_ws.p, res + 1 * ZKE_RES_G1_BLOCK, st);
+        if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MSM_B1, t0, t1}); t0 = t1; }
+        dev::MsmPlan<dev::Fq>::run(zk->C.p, w, m, x->cfg_w, L.msm_ws.p, res + 2 * ZKE_RES_G1_BLOCK, st);
+        if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MSM_C, t0, t1}); t0 = t1; }
         if (prof) {
             size_t i0, i1;
-            cudaEvent_t evs[2] = {x->ev(&i0), nullptr};
-            evs[1] = x->ev(&i1);
-            dev::MsmPlan<dev::Fq>::run(zk->H.p, x->vd.p, N, ZKE_MSM_C_H, false, x->msm_ws.p, res + 384, st, evs);
+            cudaEvent_t evs[2];
+            evs[0] = x->ev(&i0); evs[1] = x->ev(&i1);
+            dev::MsmPlan<dev::Fq>::run(zk->H.p, L.vd.p, N, x->cfg_h, L.msm_ws.p, res + 3 * ZKE_RES_G1_BLOCK, st, evs);
             x->spans.push_back({ZKE_STAGE_MSM_H_BUCKETS, i0, i1});
-            t1 = x->mark(); x->spans.push_back({ZKE_STAGE_MSM_H, t0, t1}); t0 = t1;
+            t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MSM_H, t0, t1}); t0 = t1;
         } else {
-            dev::MsmPlan<dev::Fq>::run(zk->H.p, x->vd.p, N, ZKE_MSM_C_H, false, x->msm_ws.p, res + 384, st);
+            dev::MsmPlan<dev::Fq>::run(zk->H.p, L.vd.p, N, x->cfg_h, L.msm_ws.p, res + 3 * ZKE_RES_G1_BLOCK, st);
         }
-        dev::MsmPlan<dev::Fq2>::run(zk->B2.p, w, m, ZKE_MSM_C_WITNESS, true, x->msm_ws.p, res + 512, st);
-        if (prof) { t1 = x->mark(); x->spans.push_back({ZKE_STAGE_MSM_B2, t0, t1}); t0 = t1; }
+        dev::MsmPlan<dev::Fq2>::run(zk->B2.p, w, m, x->cfg_w, L.msm_ws.p, res + 4 * ZKE_RES_G1_BLOCK, st);
+        if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MSM_B2, t0, t1}); t0 = t1; }
+        CUDA_OK(cudaMemcpyAsync(x->results_host + (size_t)ZKE_RESULT_STRIDE * e, res, ZKE_RESULT_STRIDE, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaEventRecord(x->done[e], st));
     }
-    std::vector<uint8_t> res_host(ZKE_RESULT_STRIDE * batch);
-    std::vector<uint8_t> pub_host((size_t)std::max(1u, l) * 32 * batch);
-    CUDA_OK(cudaMemcpyAsync(res_host.data(), x->results.p, res_host.size(), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(x->bad_host.data(), x->first_bad.p, 4 * batch, cudaMemcpyDeviceToHost, st));
-    if (l) CUDA_OK(cudaMemcpy2DAsync(pub_host.data(), (size_t)l * 32, x->w_all.p + 32, x->stride * 32, (size_t)l * 32, batch, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaStreamSynchronize(st));
-    if (x->profile) x->collect();
 
+    // host tail, overlapped with the GPU work of the later emails
     int bad = 0;
     const G1JacH alpha1 = G1JacH::from_affine(zk->alpha1), beta1 = G1JacH::from_affine(zk->beta1), delta1 = G1JacH::from_affine(zk->delta1);
     const G2JacH beta2 = G2JacH::from_affine(zk->beta2), delta2 = G2JacH::from_affine(zk->delta2);
     for (size_t e = 0; e < batch; ++e) {
-        int32_t s = x->bad_host[e] == 0xffffffffu ? -1 : (int32_t)x->bad_host[e];
+        CUDA_OK(cudaEventSynchronize(x->done[e]));
+        const uint8_t* res = x->results_host + (size_t)ZKE_RESULT_STRIDE * e;
+        uint32_t flag;
+        memcpy(&flag, res + ZKE_RES_FLAG_OFF, 4);
+        int32_t s = flag == 0xffffffffu ? -1 : (int32_t)flag;
         if (status) status[e] = s;
         uint8_t* out = proofs_out + 256 * e;
         if (s >= 0) {
@@ -435,11 +475,11 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
         if (rs) { memcpy(r.v, rs + 64 * e, 32); memcpy(sc.v, rs + 64 * e + 32, 32); }
         else { random_scalar(r); random_scalar(sc); }
         if (u256_cmp(r, fr_params().p) >= 0 || u256_cmp(sc, fr_params().p) >= 0) throw std::runtime_error("r / s not reduced mod the group order");
-        const uint8_t* res = res_host.data() + ZKE_RESULT_STRIDE * e;
-        G1AffineH ma, mb1, mc, mh;
-        G2AffineH mb2;
-        read_affine<Fq>(res + 0, ma); read_affine<Fq>(res + 128, mb1); read_affine<Fq>(res + 256, mc); read_affine<Fq>(res + 384, mh);
-        read_affine<Fq2>(res + 512, mb2);
+        G1AffineH ma = finish_msm<Fq>(res + 0 * ZKE_RES_G1_BLOCK, x->cfg_w);
+        G1AffineH mb1 = finish_msm<Fq>(res + 1 * ZKE_RES_G1_BLOCK, x->cfg_w);
+        G1AffineH mc = finish_msm<Fq>(res + 2 * ZKE_RES_G1_BLOCK, x->cfg_w);
+        G1AffineH mh = finish_msm<Fq>(res + 3 * ZKE_RES_G1_BLOCK, x->cfg_h);
+        G2AffineH mb2 = finish_msm<Fq2>(res + 4 * ZKE_RES_G1_BLOCK, x->cfg_w);
         // pi_A = alpha + A + r delta ; pi_B = beta + B + s delta ; pi_C = C + H + s pi_A + r pi_B1 - r s delta
         G1JacH pa = alpha1.add(G1JacH::from_affine(ma)).add(delta1.mul(r));
         G2JacH pb2 = beta2.add(G2JacH::from_affine(mb2)).add(delta2.mul(sc));
@@ -452,7 +492,11 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
         write_fq(out + 64, B.x.c0); write_fq(out + 96, B.x.c1); write_fq(out + 128, B.y.c0); write_fq(out + 160, B.y.c1);
         write_fq(out + 192, C.x); write_fq(out + 224, C.y);
     }
-    if (publics_out && l) memcpy(publics_out, pub_host.data(), (size_t)l * 32 * batch);
+    CUDA_OK(cudaStreamSynchronize(x->stream));
+    for (int i = 0; i < n_lanes; ++i) CUDA_OK(cudaStreamSynchronize(x->lanes[i].st));
+    // later work on the main stream (next witness batch) must not overtake the lanes: they are idle now
+    if (prof) x->collect();
+    if (publics_out && l) memcpy(publics_out, x->publics_host, (size_t)l * 32 * batch);
     return bad;
 }
 
@@ -538,6 +582,11 @@ void zke_ctx_close(zke_ctx* x) {
     if (!x) return;
     cudaSetDevice(x->device);
     for (auto e : x->ev_pool) cudaEventDestroy(e);
+    for (auto e : x->done) cudaEventDestroy(e);
+    if (x->witness_done) cudaEventDestroy(x->witness_done);
+    for (int i = 0; i < x->lanes_alloc; ++i) if (x->lanes[i].st) cudaStreamDestroy(x->lanes[i].st);
+    if (x->results_host) cudaFreeHost(x->results_host);
+    if (x->publics_host) cudaFreeHost(x->publics_host);
     if (x->stream) cudaStreamDestroy(x->stream);
     delete x;
 }
@@ -554,6 +603,11 @@ int zke_upload_inputs(zke_ctx* x, const uint8_t* inputs, size_t batch, char* err
     } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
 }
 
+int zke_ctx_set_lanes(zke_ctx* x, int n) {
+    if (!x || n < 1) return -1;
+    x->n_lanes = n > x->lanes_alloc ? x->lanes_alloc : n;
+    return x->n_lanes;
+}
 int zke_ctx_profile(zke_ctx* x, int enable) {
     if (!x) return -1;
     x->profile = enable != 0;

@@ -12,8 +12,10 @@ struct zke_circuit {
     zke::Circuit c;
 };
 
-// window widths (bits) of the signed-digit Pippenger: witness-scalar MSMs (mostly tiny scalars) and the H MSM
-#define ZKE_MSM_C_WITNESS 12
-#define ZKE_MSM_C_H 16
-// per-email result block on the device: A, B1, C, H (G1 XYZZ, 128 bytes each) then B2 (G2 XYZZ, 256 bytes)
-#define ZKE_RESULT_STRIDE 768
+// per-email result block: the MSM result blocks (msm.cuh: 64 XYZZ slots each) of A, B1, C, H (G1, 128-byte slots)
+// followed by B2 (G2, 256-byte slots), then the first-violated-constraint word
+#define ZKE_RES_G1_BLOCK (64 * 128)
+#define ZKE_RES_G2_BLOCK (64 * 256)
+#define ZKE_RES_FLAG_OFF (4 * ZKE_RES_G1_BLOCK + ZKE_RES_G2_BLOCK)
+#define ZKE_RESULT_STRIDE (ZKE_RES_FLAG_OFF + 256)
+#define ZKE_MAX_LANES 8

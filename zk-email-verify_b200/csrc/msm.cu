@@ -18,9 +18,9 @@
 namespace zke {
 namespace dev {
 
-static const int CHUNK = 256;       // max entries accumulated by one thread
-static const int GROUP = 64;        // buckets per running-sum thread
-static const int LIST_FANIN = 32;   // points summed per thread in the list reductions
+static const int LIST_FANIN = 32;   // affine points summed per thread at the first level of the unit-scalar reduction
+static const int TREE_FANIN = 8;    // XYZZ partial sums combined per thread at the following levels
+// (chunk = max bucket entries accumulated by one thread, group = buckets per running-sum thread: MsmConfig)
 
 __device__ __forceinline__ Fr load_scalar(const uint8_t* scalars, uint32_t i) { return Fr::load(scalars + 32ull * i); }
 
@@ -57,17 +57,26 @@ __global__ void sum_affine_list_kernel(const uint8_t* __restrict__ points, const
     acc.store(out + sizeof(XYZZ<F>) * (size_t)t);
 }
 
-// in-place tree step: out[t] = sum_{k = t, t + n_out, ...} in[k]
+// tree step: out[t] = sum_{k = t, t + n_out, ...} in[k].  The size of `in` is derived on the device from the list
+// length: level 0 has ceil(count / LIST_FANIN) partial sums, each further level divides by TREE_FANIN (min 1).
+// If pad_to > 0 this is the last level: slots [n_out, pad_to) are filled with the point at infinity.
+__device__ __forceinline__ uint32_t tree_level_size(uint32_t count, uint32_t level) {
+    uint32_t n = max(1u, (count + LIST_FANIN - 1) / LIST_FANIN);
+    for (uint32_t d = 0; d < level; ++d) n = max(1u, (n + TREE_FANIN - 1) / TREE_FANIN);
+    return n;
+}
 template <class F>
 __global__ void sum_xyzz_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ count_ptr, uint32_t count_fixed,
-                                uint32_t div, uint8_t* out) {
-    uint32_t count = count_ptr ? *count_ptr : count_fixed;
-    for (uint32_t d = 0; d < div; ++d) count = max(1u, (count + LIST_FANIN - 1) / LIST_FANIN);   // size of `in`
-    const uint32_t n_out = max(1u, (count + LIST_FANIN - 1) / LIST_FANIN);
+                                uint32_t level, uint32_t pad_to, uint8_t* out) {
+    const uint32_t count = count_ptr ? *count_ptr : count_fixed;
+    const uint32_t n_in = tree_level_size(count, level), n_out = tree_level_size(count, level + 1);
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_out) return;
+    if (t >= n_out) {
+        if (t < pad_to) XYZZ<F>::inf().store(out + sizeof(XYZZ<F>) * (size_t)t);
+        return;
+    }
     XYZZ<F> acc = XYZZ<F>::inf();
-    for (uint32_t k = t; k < count; k += n_out) acc.add(XYZZ<F>::load(in + sizeof(XYZZ<F>) * (size_t)k));
+    for (uint32_t k = t; k < n_in; k += n_out) acc.add(XYZZ<F>::load(in + sizeof(XYZZ<F>) * (size_t)k));
     acc.store(out + sizeof(XYZZ<F>) * (size_t)t);
 }
 
@@ -75,6 +84,8 @@ __global__ void sum_xyzz_kernel(const uint8_t* __restrict__ in, const uint32_t* 
 struct Digits {
     int c, n_windows;
     uint32_t half;   // 2^(c-1) buckets per window
+    uint32_t chunk;  // max bucket entries accumulated by one thread
+    uint32_t group;  // buckets per running-sum thread
 };
 
 __device__ __forceinline__ uint32_t window_bits(const Fr& s, int bit, int c) {
@@ -126,15 +137,30 @@ __global__ void digit_scatter_kernel(const uint8_t* __restrict__ scalars, const 
     }
 }
 
-// ---------------------------------------------------------------- single-block exclusive scan (n up to a few million)
-// out[i] = sum_{k<i} f(in[k]); out[n] = total.  f = identity (mode 0) or ceil(x / CHUNK) (mode 1)
-__global__ void __launch_bounds__(1024) scan_kernel(const uint32_t* __restrict__ in, uint32_t n, int mode, uint32_t* out) {
+// ---------------------------------------------------------------- exclusive scan over the bucket array
+// out[i] = sum_{k<i} f(in[k]); out[n] = total.  f = identity (chunk == 0) or ceil(x / chunk).
+// Three phases: per-tile totals, single-block scan of the tile totals, per-tile rescan with the tile's base.
+static const int SCAN_TILE = 2048;   // elements per block (256 threads x 8)
+__device__ __forceinline__ uint32_t scan_f(uint32_t v, uint32_t chunk) { return chunk ? (v + chunk - 1) / chunk : v; }
+
+__global__ void __launch_bounds__(256) scan_tile_totals_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t chunk, uint32_t* tile_sums) {
+    __shared__ uint32_t red[256];
+    const uint32_t base = blockIdx.x * SCAN_TILE;
+    uint32_t local = 0;
+    for (uint32_t i = threadIdx.x; i < SCAN_TILE; i += 256) if (base + i < n) local += scan_f(in[base + i], chunk);
+    red[threadIdx.x] = local;
+    __syncthreads();
+    for (uint32_t off = 128; off > 0; off >>= 1) { if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off]; __syncthreads(); }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = red[0];
+}
+// exclusive scan of up to 1024 * 8 values in one block (in place)
+__global__ void __launch_bounds__(1024) scan_small_kernel(uint32_t* data, uint32_t n, uint32_t* total_out) {
     __shared__ uint32_t sums[1024];
     const uint32_t tid = threadIdx.x;
     const uint32_t per = (n + 1023) / 1024;
-    const uint32_t beg = tid * per, end = min(n, beg + per);
+    const uint32_t beg = min(n, tid * per), end = min(n, beg + per);
     uint32_t local = 0;
-    for (uint32_t i = beg; i < end; ++i) { uint32_t v = in[i]; local += mode ? (v + CHUNK - 1) / CHUNK : v; }
+    for (uint32_t i = beg; i < end; ++i) local += data[i];
     sums[tid] = local;
     __syncthreads();
     for (uint32_t off = 1; off < 1024; off <<= 1) {
@@ -144,12 +170,38 @@ __global__ void __launch_bounds__(1024) scan_kernel(const uint32_t* __restrict__
         __syncthreads();
     }
     uint32_t run = sums[tid] - local;
-    for (uint32_t i = beg; i < end; ++i) { uint32_t v = in[i]; out[i] = run; run += mode ? (v + CHUNK - 1) / CHUNK : v; }
-    if (tid == 1023) out[n] = sums[1023];
+    for (uint32_t i = beg; i < end; ++i) { uint32_t v = data[i]; data[i] = run; run += v; }
+    if (tid == 1023 && total_out) *total_out = sums[1023];
+}
+__global__ void __launch_bounds__(256) scan_tile_apply_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t chunk,
+                                                              const uint32_t* __restrict__ tile_base, uint32_t* out) {
+    __shared__ uint32_t sums[256];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+    uint32_t v[8], local = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { v[k] = (base + k < n) ? scan_f(in[base + k], chunk) : 0; local += v[k]; }
+    sums[threadIdx.x] = local;
+    __syncthreads();
+    for (uint32_t off = 1; off < 256; off <<= 1) {
+        uint32_t x = threadIdx.x >= off ? sums[threadIdx.x - off] : 0;
+        __syncthreads();
+        sums[threadIdx.x] += x;
+        __syncthreads();
+    }
+    uint32_t run = tile_base[blockIdx.x] + sums[threadIdx.x] - local;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { if (base + k < n) out[base + k] = run; run += v[k]; }
+}
+// host helper: `tiles` is scratch for ceil(n / SCAN_TILE) + 1 words
+static void exclusive_scan(const uint32_t* in, uint32_t n, uint32_t chunk, uint32_t* out, uint32_t* tiles, cudaStream_t st) {
+    const uint32_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    scan_tile_totals_kernel<<<n_tiles, 256, 0, st>>>(in, n, chunk, tiles);
+    scan_small_kernel<<<1, 1024, 0, st>>>(tiles, n_tiles, out + n);
+    scan_tile_apply_kernel<<<n_tiles, 256, 0, st>>>(in, n, chunk, tiles, out);
 }
 
 __global__ void fill_work_kernel(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off, uint32_t n_buckets,
-                                 uint32_t* work_bucket) {
+                                 uint32_t CHUNK, uint32_t* work_bucket) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_buckets) return;
     const uint32_t nch = (hist[b] + CHUNK - 1) / CHUNK;
@@ -161,7 +213,7 @@ template <class F>
 __global__ void __launch_bounds__(128)
 chunk_sum_kernel(const uint8_t* __restrict__ points, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
                  const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off, const uint32_t* __restrict__ work_bucket,
-                 uint32_t n_buckets, uint8_t* partial) {
+                 uint32_t n_buckets, uint32_t CHUNK, uint8_t* partial) {
     const uint32_t total = chunk_off[n_buckets];
     for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
         const uint32_t b = work_bucket[w];
@@ -182,7 +234,7 @@ chunk_sum_kernel(const uint8_t* __restrict__ points, const uint32_t* __restrict_
 template <class F>
 __global__ void __launch_bounds__(128)
 group_sum_kernel(const uint8_t* __restrict__ partial, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off,
-                 uint32_t half, uint32_t n_groups_total, uint8_t* group_out) {
+                 uint32_t half, uint32_t n_groups_total, uint32_t CHUNK, uint32_t GROUP, uint8_t* group_out) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups_total) return;
     const uint32_t groups_per_window = (half + GROUP - 1) / GROUP;
@@ -225,31 +277,31 @@ window_reduce_kernel(uint8_t* group_out, uint32_t groups_per_window) {
     }
 }
 
-// result = ones_sum + sum_j 2^(c j) window_j
+// copies slot 0 of every window (the reduced window sum) into the MSM's result block
 template <class F>
-__global__ void msm_final_kernel(const uint8_t* __restrict__ group_out, uint32_t groups_per_window, Digits D,
-                                 const uint8_t* __restrict__ ones_sum, int have_pippenger, uint8_t* result) {
-    if (threadIdx.x || blockIdx.x) return;
-    XYZZ<F> acc = XYZZ<F>::inf();
-    if (have_pippenger) {
-        for (int j = D.n_windows - 1; j >= 0; --j) {
-            for (int k = 0; k < D.c; ++k) acc.dbl();
-            acc.add(XYZZ<F>::load(group_out + sizeof(XYZZ<F>) * (size_t)j * groups_per_window));
-        }
-    }
-    if (ones_sum) acc.add(XYZZ<F>::load(ones_sum));
-    acc.store(result);
+__global__ void gather_windows_kernel(const uint8_t* __restrict__ group_out, uint32_t groups_per_window, uint32_t n_windows, uint8_t* out) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_windows) return;
+    XYZZ<F>::load(group_out + sizeof(XYZZ<F>) * (size_t)j * groups_per_window).store(out + sizeof(XYZZ<F>) * (size_t)j);
 }
 
 // ---------------------------------------------------------------- host orchestration
+MsmConfig msm_config_witness() { MsmConfig c; c.c = 8; c.chunk = 32; c.group = 8; c.classify = true; return c; }
+MsmConfig msm_config_full(uint32_t n) {
+    MsmConfig c;
+    c.c = n >= (1u << 18) ? 16 : (n >= (1u << 12) ? 12 : 8);
+    c.chunk = 256; c.group = 16; c.classify = false;
+    return c;
+}
+
 template <class F>
-size_t MsmPlan<F>::workspace_bytes(uint32_t n, int c) {
-    const int W = (255 + c - 1) / c;
-    const size_t half = (size_t)1 << (c - 1);
+size_t MsmPlan<F>::workspace_bytes(uint32_t n, const MsmConfig& cfg) {
+    const int W = (255 + cfg.c - 1) / cfg.c;
+    const size_t half = (size_t)1 << (cfg.c - 1);
     const size_t n_buckets = half * W;
     const size_t max_entries = (size_t)n * W;
-    const size_t max_chunks = n_buckets + max_entries / CHUNK + 1;
-    const size_t groups = ((half + GROUP - 1) / GROUP) * W;
+    const size_t max_chunks = n_buckets + max_entries / cfg.chunk + 1;
+    const size_t groups = ((half + cfg.group - 1) / cfg.group) * W;
     size_t b = 0;
     auto al = [&](size_t x) { b += (x + 255) & ~(size_t)255; };
     al(4 * 2);                         // counters
@@ -259,6 +311,7 @@ size_t MsmPlan<F>::workspace_bytes(uint32_t n, int c) {
     al(4 * (n_buckets + 1));           // offsets
     al(4 * (n_buckets + 1));           // cursor
     al(4 * (n_buckets + 1));           // chunk_off
+    al(4 * (n_buckets / SCAN_TILE + 2));  // scan tiles
     al(4 * max_entries);               // entries
     al(4 * max_chunks);                // work_bucket
     al(sizeof(XYZZ<F>) * max_chunks);  // partial
@@ -268,16 +321,19 @@ size_t MsmPlan<F>::workspace_bytes(uint32_t n, int c) {
 }
 
 template <class F>
-void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, int c, bool classify, uint8_t* ws,
+void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, const MsmConfig& cfg, uint8_t* ws,
                      uint8_t* result, cudaStream_t st, cudaEvent_t* ev) {
     Digits D;
-    D.c = c;
-    D.n_windows = (255 + c - 1) / c;
-    D.half = 1u << (c - 1);
+    D.c = cfg.c;
+    D.n_windows = (255 + cfg.c - 1) / cfg.c;
+    D.half = 1u << (cfg.c - 1);
+    D.chunk = cfg.chunk;
+    D.group = cfg.group;
+    if (D.n_windows > MSM_MAX_WINDOWS) return;
     const uint32_t n_buckets = D.half * D.n_windows;
     const size_t max_entries = (size_t)n * D.n_windows;
-    const size_t max_chunks = n_buckets + max_entries / CHUNK + 1;
-    const uint32_t groups_per_window = (D.half + GROUP - 1) / GROUP;
+    const size_t max_chunks = n_buckets + max_entries / cfg.chunk + 1;
+    const uint32_t groups_per_window = (D.half + D.group - 1) / D.group;
     const uint32_t groups = groups_per_window * D.n_windows;
     uint8_t* p = ws;
     auto take = [&](size_t x) { uint8_t* r = p; p += (x + 255) & ~(size_t)255; return r; };
@@ -288,6 +344,7 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     uint32_t* offsets = (uint32_t*)take(4 * ((size_t)n_buckets + 1));
     uint32_t* cursor = (uint32_t*)take(4 * ((size_t)n_buckets + 1));
     uint32_t* chunk_off = (uint32_t*)take(4 * ((size_t)n_buckets + 1));
+    uint32_t* tiles = (uint32_t*)take(4 * ((size_t)n_buckets / SCAN_TILE + 2));
     uint32_t* entries = (uint32_t*)take(4 * max_entries);
     uint32_t* work_bucket = (uint32_t*)take(4 * max_chunks);
     uint8_t* partial = take(sizeof(XYZZ<F>) * max_chunks);
@@ -296,29 +353,35 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     uint8_t* red_a = take(sizeof(XYZZ<F>) * list_slots);
     uint8_t* red_b = take(sizeof(XYZZ<F>) * list_slots);
 
+    // result block: [MSM_ONES_SLOTS partial sums of the unit-scalar points][MSM_MAX_WINDOWS window sums]
+    uint8_t* res_ones = result;
+    uint8_t* res_windows = result + sizeof(XYZZ<F>) * MSM_ONES_SLOTS;
+    cudaMemsetAsync(result, 0, sizeof(XYZZ<F>) * MSM_RESULT_SLOTS, st);   // all-zero XYZZ = infinity
+
     const uint32_t* gen_count = nullptr;
     const uint32_t* gen_idx = nullptr;
-    const uint8_t* ones_sum = nullptr;
-    if (classify) {
+    if (cfg.classify) {
         cudaMemsetAsync(counters, 0, 8, st);
         classify_kernel<F><<<(n + 255) / 256, 256, 0, st>>>(points, scalars, n, ones_list, gen_list, counters);
+        // unit scalars: tree reduction; level sizes are recomputed on the device from counters[0], the host only
+        // needs the upper bound n to know how many levels to launch
+        uint32_t upper = (n + LIST_FANIN - 1) / LIST_FANIN;
+        sum_affine_list_kernel<F><<<(upper + 127) / 128, 128, 0, st>>>(points, ones_list, counters, 0, red_a);
         ZKE_COUNT_LAUNCH(2);
-        // ones: tree reduction with fan-in LIST_FANIN; level sizes are computed on the device from counters[0]
-        uint32_t upper = n;
-        uint32_t lvl_out = (upper + LIST_FANIN - 1) / LIST_FANIN;
-        sum_affine_list_kernel<F><<<(lvl_out + 127) / 128, 128, 0, st>>>(points, ones_list, counters, 0, red_a);
         uint8_t *src = red_a, *dst = red_b;
-        uint32_t div = 1;
-        upper = lvl_out;
-        while (upper > 1) {
-            lvl_out = (upper + LIST_FANIN - 1) / LIST_FANIN;
-            sum_xyzz_kernel<F><<<(lvl_out + 127) / 128, 128, 0, st>>>(src, counters, 0, div, dst);
+        uint32_t level = 0;
+        for (;;) {
+            const uint32_t next = (upper + TREE_FANIN - 1) / TREE_FANIN;
+            const bool last = next <= MSM_ONES_SLOTS;
+            uint8_t* out = last ? res_ones : dst;
+            const uint32_t threads = last ? (uint32_t)MSM_ONES_SLOTS : next;
+            sum_xyzz_kernel<F><<<(threads + 63) / 64, 64, 0, st>>>(src, counters, 0, level, last ? MSM_ONES_SLOTS : 0, out);
             ZKE_COUNT_LAUNCH(1);
+            if (last) break;
             uint8_t* t = src; src = dst; dst = t;
-            upper = lvl_out;
-            ++div;
+            upper = next;
+            ++level;
         }
-        ones_sum = src;   // slot 0 (the point at infinity if the list was empty)
         gen_count = counters + 1;
         gen_idx = gen_list;
     }
@@ -326,17 +389,17 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     cudaMemsetAsync(cursor, 0, 4 * ((size_t)n_buckets + 1), st);
     const int grid = 148 * 8;
     digit_hist_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, hist);
-    scan_kernel<<<1, 1024, 0, st>>>(hist, n_buckets, 0, offsets);
+    exclusive_scan(hist, n_buckets, 0, offsets, tiles, st);
     digit_scatter_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, offsets, cursor, entries);
-    scan_kernel<<<1, 1024, 0, st>>>(hist, n_buckets, 1, chunk_off);
-    fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, chunk_off, n_buckets, work_bucket);
+    exclusive_scan(hist, n_buckets, D.chunk, chunk_off, tiles, st);
+    fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, chunk_off, n_buckets, D.chunk, work_bucket);
     if (ev) cudaEventRecord(ev[0], st);
-    chunk_sum_kernel<F><<<148 * 16, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, partial);
+    chunk_sum_kernel<F><<<148 * 16, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
     if (ev) cudaEventRecord(ev[1], st);
-    group_sum_kernel<F><<<(groups + 127) / 128, 128, 0, st>>>(partial, hist, chunk_off, D.half, groups, group_out);
+    group_sum_kernel<F><<<(groups + 127) / 128, 128, 0, st>>>(partial, hist, chunk_off, D.half, groups, D.chunk, D.group, group_out);
     window_reduce_kernel<F><<<D.n_windows, 512, 0, st>>>(group_out, groups_per_window);
-    msm_final_kernel<F><<<1, 32, 0, st>>>(group_out, groups_per_window, D, ones_sum, 1, result);
-    ZKE_COUNT_LAUNCH(9);
+    gather_windows_kernel<F><<<1, 64, 0, st>>>(group_out, groups_per_window, D.n_windows, res_windows);
+    ZKE_COUNT_LAUNCH(13);
 }
 
 template struct MsmPlan<Fq>;

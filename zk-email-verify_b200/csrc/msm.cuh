@@ -4,18 +4,34 @@
 namespace zke {
 namespace dev {
 
+struct MsmConfig {
+    int c = 16;            // signed window width in bits
+    uint32_t chunk = 256;  // max bucket entries accumulated by one thread
+    uint32_t group = 16;   // buckets per running-sum thread
+    bool classify = false; // true: drop zero scalars / infinite points and sum unit scalars outside the buckets
+};
+MsmConfig msm_config_witness();          // witness-scalar MSMs (mostly 0 / 1 / byte-sized scalars)
+MsmConfig msm_config_full(uint32_t n);   // full-width scalars (the H MSM)
+
+// Result block of one MSM (device or host memory), XYZZ points:
+//   slots [0, MSM_ONES_SLOTS)                 partial sums of the unit-scalar points (infinity-padded)
+//   slots [MSM_ONES_SLOTS, +n_windows)        per-window bucket sums S_j; the MSM value is
+//                                             sum(ones) + sum_j 2^(c j) S_j  - the short serial tail (Horner over the
+//                                             windows, ~255 doublings) is left to the host, which does it ~20x faster
+//                                             than a single GPU thread.
+static const int MSM_ONES_SLOTS = 32;
+static const int MSM_MAX_WINDOWS = 32;
+static const int MSM_RESULT_SLOTS = MSM_ONES_SLOTS + MSM_MAX_WINDOWS;
+
 // Multi-scalar multiplication sum_i scalars[i] * points[i] over G1 (F = Fq) or G2 (F = Fq2).
 //   points  : n affine points (Montgomery coordinates), (0,0) = infinity
 //   scalars : n x 32-byte standard-form little-endian integers < r
-//   c       : window width in bits (signed digits)
-//   classify: true -> zero scalars / infinite points are skipped and unit scalars are summed outside the bucket
-//             machinery (witness MSMs); false -> every scalar goes through Pippenger (the H MSM)
-//   result  : one XYZZ point (device memory)
+//   result  : MSM_RESULT_SLOTS XYZZ points (device memory), layout above
 template <class F>
 struct MsmPlan {
-    static size_t workspace_bytes(uint32_t n, int c);
+    static size_t workspace_bytes(uint32_t n, const MsmConfig& cfg);
     // ev (optional): two events recorded immediately before / after the bucket-accumulation kernel (profiling)
-    static void run(const uint8_t* points, const uint8_t* scalars, uint32_t n, int c, bool classify, uint8_t* workspace,
+    static void run(const uint8_t* points, const uint8_t* scalars, uint32_t n, const MsmConfig& cfg, uint8_t* workspace,
                     uint8_t* result, cudaStream_t st, cudaEvent_t* ev = nullptr);
 };
 

@@ -78,6 +78,7 @@ zke_pack_inputs_json = _sig("zke_pack_inputs_json", c_int, [c_void_p, c_char_p, 
 zke_fullprove_json = _sig("zke_fullprove_json", c_int, [c_void_p, c_void_p, c_char_p, c_char_p, ctypes.POINTER(c_size_t), c_char_p,
                                                         ctypes.POINTER(c_size_t), c_char_p, c_size_t])
 zke_upload_inputs = _sig("zke_upload_inputs", c_int, [c_void_p, c_void_p, c_size_t, c_char_p, c_size_t])
+zke_ctx_set_lanes = _sig("zke_ctx_set_lanes", c_int, [c_void_p, c_int])
 zke_ctx_profile = _sig("zke_ctx_profile", c_int, [c_void_p, c_int])
 zke_ctx_profile_get = _sig("zke_ctx_profile_get", c_int, [c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_u64)])
 STAGES = ("witness", "matvec", "ntt", "msm_a", "msm_b1", "msm_c", "msm_h", "msm_h_buckets", "msm_b2")
