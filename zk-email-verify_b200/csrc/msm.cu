@@ -95,19 +95,41 @@ __device__ __forceinline__ uint32_t window_bits(const Fr& s, int bit, int c) {
     return (uint32_t)((two >> b) & ((1u << c) - 1));
 }
 
-// calls f(window, bucket_in_window, negative) for every non-zero signed digit
+// Scalars above r/2 are replaced by r - s with the point negated: "negative" witness values (index differences,
+// signed carries, -1 coefficients folded into signals) then have one or two non-zero digits instead of 32 identical
+// high digits that would all land in the same few buckets.
+__device__ __forceinline__ bool minimal_magnitude(Fr& s) {
+    const FieldConsts& C = FR_C;
+    // s > (r-1)/2  <=>  2s >= r + 1  <=> 2s > r
+    Fr n;
+    n.v[0] = sub_cc(C.mod[0], s.v[0]);
+#pragma unroll
+    for (int i = 1; i < 8; ++i) n.v[i] = subc_cc(C.mod[i], s.v[i]);
+    (void)subc(0, 0);
+    // compare n < s (n = r - s): lexicographic from the top limb
+    bool less = false, decided = false;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        if (!decided && n.v[i] != s.v[i]) { less = n.v[i] < s.v[i]; decided = true; }
+    }
+    if (less) { s = n; return true; }
+    return false;
+}
+
+// calls f(window, bucket_in_window, negative) for every non-zero signed digit of (+/-) s
 template <class Fn>
-__device__ __forceinline__ void for_each_digit(const Fr& s, const Digits& D, Fn f) {
+__device__ __forceinline__ void for_each_digit(Fr s, const Digits& D, Fn f) {
+    const bool flip = minimal_magnitude(s);
     uint32_t carry = 0;
     for (int j = 0; j < D.n_windows; ++j) {
         uint32_t raw = window_bits(s, j * D.c, D.c) + carry;
         if (raw > D.half) {                      // digit = raw - 2^c  (negative or zero), carry 1
             carry = 1;
             const uint32_t mag = (1u << D.c) - raw;   // raw == 2^c (all-ones window plus carry) gives digit 0
-            if (mag) f(j, mag - 1, true);
+            if (mag) f(j, mag - 1, !flip);
         } else {
             carry = 0;
-            if (raw) f(j, raw - 1, false);
+            if (raw) f(j, raw - 1, flip);
         }
     }
 }
@@ -141,13 +163,21 @@ __global__ void digit_scatter_kernel(const uint8_t* __restrict__ scalars, const 
 // out[i] = sum_{k<i} f(in[k]); out[n] = total.  f = identity (chunk == 0) or ceil(x / chunk).
 // Three phases: per-tile totals, single-block scan of the tile totals, per-tile rescan with the tile's base.
 static const int SCAN_TILE = 2048;   // elements per block (256 threads x 8)
-__device__ __forceinline__ uint32_t scan_f(uint32_t v, uint32_t chunk) { return chunk ? (v + chunk - 1) / chunk : v; }
+static const uint32_t PASS_FANIN = 32;   // partial sums combined per thread in the extra reduction passes
+// number of items a bucket with v entries has after the first pass (chunks of `chunk` entries) and `levels` further
+// passes of fan-in PASS_FANIN; chunk == 0 means "the raw entry count"
+__device__ __forceinline__ uint32_t scan_f(uint32_t v, uint32_t chunk, uint32_t levels = 0) {
+    if (!chunk) return v;
+    v = (v + chunk - 1) / chunk;
+    for (uint32_t l = 0; l < levels; ++l) v = (v + PASS_FANIN - 1) / PASS_FANIN;
+    return v;
+}
 
-__global__ void __launch_bounds__(256) scan_tile_totals_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t chunk, uint32_t* tile_sums) {
+__global__ void __launch_bounds__(256) scan_tile_totals_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t chunk, uint32_t levels, uint32_t* tile_sums) {
     __shared__ uint32_t red[256];
     const uint32_t base = blockIdx.x * SCAN_TILE;
     uint32_t local = 0;
-    for (uint32_t i = threadIdx.x; i < SCAN_TILE; i += 256) if (base + i < n) local += scan_f(in[base + i], chunk);
+    for (uint32_t i = threadIdx.x; i < SCAN_TILE; i += 256) if (base + i < n) local += scan_f(in[base + i], chunk, levels);
     red[threadIdx.x] = local;
     __syncthreads();
     for (uint32_t off = 128; off > 0; off >>= 1) { if (threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off]; __syncthreads(); }
@@ -173,13 +203,13 @@ __global__ void __launch_bounds__(1024) scan_small_kernel(uint32_t* data, uint32
     for (uint32_t i = beg; i < end; ++i) { uint32_t v = data[i]; data[i] = run; run += v; }
     if (tid == 1023 && total_out) *total_out = sums[1023];
 }
-__global__ void __launch_bounds__(256) scan_tile_apply_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t chunk,
+__global__ void __launch_bounds__(256) scan_tile_apply_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t chunk, uint32_t levels,
                                                               const uint32_t* __restrict__ tile_base, uint32_t* out) {
     __shared__ uint32_t sums[256];
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 8;
     uint32_t v[8], local = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { v[k] = (base + k < n) ? scan_f(in[base + k], chunk) : 0; local += v[k]; }
+    for (int k = 0; k < 8; ++k) { v[k] = (base + k < n) ? scan_f(in[base + k], chunk, levels) : 0; local += v[k]; }
     sums[threadIdx.x] = local;
     __syncthreads();
     for (uint32_t off = 1; off < 256; off <<= 1) {
@@ -193,18 +223,19 @@ __global__ void __launch_bounds__(256) scan_tile_apply_kernel(const uint32_t* __
     for (int k = 0; k < 8; ++k) { if (base + k < n) out[base + k] = run; run += v[k]; }
 }
 // host helper: `tiles` is scratch for ceil(n / SCAN_TILE) + 1 words
-static void exclusive_scan(const uint32_t* in, uint32_t n, uint32_t chunk, uint32_t* out, uint32_t* tiles, cudaStream_t st) {
+static void exclusive_scan(const uint32_t* in, uint32_t n, uint32_t chunk, uint32_t levels, uint32_t* out, uint32_t* tiles, cudaStream_t st) {
     const uint32_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    scan_tile_totals_kernel<<<n_tiles, 256, 0, st>>>(in, n, chunk, tiles);
+    scan_tile_totals_kernel<<<n_tiles, 256, 0, st>>>(in, n, chunk, levels, tiles);
     scan_small_kernel<<<1, 1024, 0, st>>>(tiles, n_tiles, out + n);
-    scan_tile_apply_kernel<<<n_tiles, 256, 0, st>>>(in, n, chunk, tiles, out);
+    scan_tile_apply_kernel<<<n_tiles, 256, 0, st>>>(in, n, chunk, levels, tiles, out);
+    ZKE_COUNT_LAUNCH(3);
 }
 
 __global__ void fill_work_kernel(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off, uint32_t n_buckets,
-                                 uint32_t CHUNK, uint32_t* work_bucket) {
+                                 uint32_t CHUNK, uint32_t levels, uint32_t* work_bucket) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_buckets) return;
-    const uint32_t nch = (hist[b] + CHUNK - 1) / CHUNK;
+    const uint32_t nch = scan_f(hist[b], CHUNK, levels);
     for (uint32_t i = 0; i < nch; ++i) work_bucket[chunk_off[b] + i] = b;
 }
 
@@ -229,12 +260,32 @@ chunk_sum_kernel(const uint8_t* __restrict__ points, const uint32_t* __restrict_
     }
 }
 
+// extra reduction pass: level `level` items of a bucket (XYZZ partial sums, contiguous at off_in[b]) are combined
+// PASS_FANIN at a time into level + 1 items at off_out[b]; spreads the partial sums of a heavy bucket (many equal
+// small scalars) over threads instead of leaving them to the running-sum thread
+template <class F>
+__global__ void __launch_bounds__(128)
+partial_pass_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ off_in,
+                    const uint32_t* __restrict__ off_out, const uint32_t* __restrict__ work_bucket, uint32_t n_buckets,
+                    uint32_t CHUNK, uint32_t level, uint8_t* out) {
+    const uint32_t total = off_out[n_buckets];
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+        const uint32_t b = work_bucket[w];
+        const uint32_t i = w - off_out[b];
+        const uint32_t n_in = scan_f(hist[b], CHUNK, level);
+        const uint32_t beg = off_in[b] + i * PASS_FANIN, end = min(off_in[b] + n_in, beg + PASS_FANIN);
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t k = beg; k < end; ++k) acc.add(XYZZ<F>::load(in + sizeof(XYZZ<F>) * (size_t)k));
+        acc.store(out + sizeof(XYZZ<F>) * (size_t)w);
+    }
+}
+
 // one thread per GROUP consecutive buckets of one window: sum_b (b+1) B_b restricted to the group, as
 // T + first_index * S with T the in-group weighted sum and S the plain sum
 template <class F>
 __global__ void __launch_bounds__(128)
 group_sum_kernel(const uint8_t* __restrict__ partial, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off,
-                 uint32_t half, uint32_t n_groups_total, uint32_t CHUNK, uint32_t GROUP, uint8_t* group_out) {
+                 uint32_t half, uint32_t n_groups_total, uint32_t CHUNK, uint32_t levels, uint32_t GROUP, uint8_t* group_out) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups_total) return;
     const uint32_t groups_per_window = (half + GROUP - 1) / GROUP;
@@ -243,7 +294,7 @@ group_sum_kernel(const uint8_t* __restrict__ partial, const uint32_t* __restrict
     XYZZ<F> running = XYZZ<F>::inf(), total = XYZZ<F>::inf();
     for (uint32_t b = hi; b-- > lo;) {
         const uint32_t bucket = window * half + b;
-        const uint32_t nch = (hist[bucket] + CHUNK - 1) / CHUNK;
+        const uint32_t nch = scan_f(hist[bucket], CHUNK, levels);
         for (uint32_t i = 0; i < nch; ++i) running.add(XYZZ<F>::load(partial + sizeof(XYZZ<F>) * (size_t)(chunk_off[bucket] + i)));
         total.add(running);
     }
@@ -286,11 +337,11 @@ __global__ void gather_windows_kernel(const uint8_t* __restrict__ group_out, uin
 }
 
 // ---------------------------------------------------------------- host orchestration
-MsmConfig msm_config_witness() { MsmConfig c; c.c = 8; c.chunk = 32; c.group = 8; c.classify = true; return c; }
+MsmConfig msm_config_witness() { MsmConfig c; c.c = 8; c.chunk = 32; c.group = 8; c.classify = true; c.extra_passes = 2; return c; }
 MsmConfig msm_config_full(uint32_t n) {
     MsmConfig c;
     c.c = n >= (1u << 18) ? 16 : (n >= (1u << 12) ? 12 : 8);
-    c.chunk = 256; c.group = 16; c.classify = false;
+    c.chunk = 256; c.group = 16; c.classify = false; c.extra_passes = 0;
     return c;
 }
 
@@ -315,6 +366,8 @@ size_t MsmPlan<F>::workspace_bytes(uint32_t n, const MsmConfig& cfg) {
     al(4 * max_entries);               // entries
     al(4 * max_chunks);                // work_bucket
     al(sizeof(XYZZ<F>) * max_chunks);  // partial
+    al(sizeof(XYZZ<F>) * (max_chunks / PASS_FANIN + n_buckets + 1));  // partial (ping-pong for the extra passes)
+    al(4 * (n_buckets + 1));           // second offsets array
     al(sizeof(XYZZ<F>) * groups);      // group sums
     al(sizeof(XYZZ<F>) * ((size_t)n / LIST_FANIN + 2) * 2);  // list reduction ping-pong
     return b;
@@ -348,6 +401,8 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     uint32_t* entries = (uint32_t*)take(4 * max_entries);
     uint32_t* work_bucket = (uint32_t*)take(4 * max_chunks);
     uint8_t* partial = take(sizeof(XYZZ<F>) * max_chunks);
+    uint8_t* partial2 = take(sizeof(XYZZ<F>) * (max_chunks / PASS_FANIN + n_buckets + 1));
+    uint32_t* off2 = (uint32_t*)take(4 * ((size_t)n_buckets + 1));
     uint8_t* group_out = take(sizeof(XYZZ<F>) * groups);
     const size_t list_slots = (size_t)n / LIST_FANIN + 2;
     uint8_t* red_a = take(sizeof(XYZZ<F>) * list_slots);
@@ -389,17 +444,30 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     cudaMemsetAsync(cursor, 0, 4 * ((size_t)n_buckets + 1), st);
     const int grid = 148 * 8;
     digit_hist_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, hist);
-    exclusive_scan(hist, n_buckets, 0, offsets, tiles, st);
+    exclusive_scan(hist, n_buckets, 0, 0, offsets, tiles, st);
     digit_scatter_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, offsets, cursor, entries);
-    exclusive_scan(hist, n_buckets, D.chunk, chunk_off, tiles, st);
-    fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, chunk_off, n_buckets, D.chunk, work_bucket);
+    exclusive_scan(hist, n_buckets, D.chunk, 0, chunk_off, tiles, st);
+    fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, chunk_off, n_buckets, D.chunk, 0, work_bucket);
     if (ev) cudaEventRecord(ev[0], st);
     chunk_sum_kernel<F><<<148 * 16, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
     if (ev) cudaEventRecord(ev[1], st);
-    group_sum_kernel<F><<<(groups + 127) / 128, 128, 0, st>>>(partial, hist, chunk_off, D.half, groups, D.chunk, D.group, group_out);
+    // extra passes over the per-chunk partial sums
+    uint8_t *items = partial, *items_next = partial2;
+    uint32_t *off_cur = chunk_off, *off_next = off2;
+    uint32_t levels = 0;
+    for (uint32_t pass = 0; pass < cfg.extra_passes; ++pass) {
+        exclusive_scan(hist, n_buckets, D.chunk, levels + 1, off_next, tiles, st);
+        fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, off_next, n_buckets, D.chunk, levels + 1, work_bucket);
+        partial_pass_kernel<F><<<148 * 4, 128, 0, st>>>(items, hist, off_cur, off_next, work_bucket, n_buckets, D.chunk, levels, items_next);
+        ZKE_COUNT_LAUNCH(2);
+        uint8_t* t = items; items = items_next; items_next = t;
+        uint32_t* o = off_cur; off_cur = off_next; off_next = o;
+        ++levels;
+    }
+    group_sum_kernel<F><<<(groups + 127) / 128, 128, 0, st>>>(items, hist, off_cur, D.half, groups, D.chunk, levels, D.group, group_out);
     window_reduce_kernel<F><<<D.n_windows, 512, 0, st>>>(group_out, groups_per_window);
     gather_windows_kernel<F><<<1, 64, 0, st>>>(group_out, groups_per_window, D.n_windows, res_windows);
-    ZKE_COUNT_LAUNCH(13);
+    ZKE_COUNT_LAUNCH(7);
 }
 
 template struct MsmPlan<Fq>;

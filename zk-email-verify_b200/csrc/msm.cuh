@@ -9,6 +9,7 @@ struct MsmConfig {
     uint32_t chunk = 256;  // max bucket entries accumulated by one thread
     uint32_t group = 16;   // buckets per running-sum thread
     bool classify = false; // true: drop zero scalars / infinite points and sum unit scalars outside the buckets
+    uint32_t extra_passes = 0;  // further fan-in-32 reductions of the per-chunk partial sums (skewed buckets)
 };
 MsmConfig msm_config_witness();          // witness-scalar MSMs (mostly 0 / 1 / byte-sized scalars)
 MsmConfig msm_config_full(uint32_t n);   // full-width scalars (the H MSM)
