@@ -104,39 +104,66 @@ struct Fp {
     __device__ __forceinline__ Fp neg() const { return is_zero() ? *this : (zero() - *this); }
     __device__ __forceinline__ Fp dbl() const { return *this + *this; }
 
-    // Montgomery product a*b/2^256 mod p (CIOS, operands < p, p < 2^254 so 9 words suffice)
-    friend __device__ __forceinline__ Fp operator*(const Fp& a, const Fp& b) {
+    // ---- Montgomery product a*b/2^256 mod p -------------------------------------------------------------------
+    // Even/odd accumulator formulation: the running total is kept as two interleaved vectors, `even` (limb k at
+    // position k) and `odd` (limb k at position k + 1), so that every 32x32 product (lo, hi) lands on an ALIGNED
+    // register pair of one of them.  Each `mad.lo.cc / madc.hi.cc` pair on such a register pair is fused by ptxas
+    // into a single 64-bit IMAD.WIDE with carry, instead of the IMAD + IADD3.X pair a limb-serial CIOS chain needs:
+    // ~20 issue slots per row instead of ~68.  After each row the low limb of `even` is
+    // zero (Montgomery step), the roles of the two vectors swap and the former `even` is realigned by the
+    // shift-by-two inside madc_n_rshift.
+    static __device__ __forceinline__ void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2)
+            asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=r"(acc[j]), "=r"(acc[j + 1]) : "r"(a[j]), "r"(bi));
+    }
+    // acc[0..8) += a[0,2,4,6] * bi (pairs), carry chained; the final carry is left in CC
+    static __device__ __forceinline__ void cmad_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+        asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[0]), "+r"(acc[1]) : "r"(a[0]), "r"(bi));
+#pragma unroll
+        for (int j = 2; j < 8; j += 2)
+            asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(acc[j]), "+r"(acc[j + 1]) : "r"(a[j]), "r"(bi));
+    }
+    // odd[j], odd[j+1] = a[j] * bi + odd[j+2], odd[j+3] (+ incoming carry): multiply-accumulate and shift down two limbs
+    static __device__ __forceinline__ void madc_n_rshift(uint32_t* odd, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+        for (int j = 0; j < 6; j += 2)
+            asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;"
+                         : "=r"(odd[j]), "=r"(odd[j + 1]) : "r"(a[j]), "r"(bi), "r"(odd[j + 2]), "r"(odd[j + 3]));
+        asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=r"(odd[6]), "=r"(odd[7]) : "r"(a[6]), "r"(bi));
+    }
+    template <bool FIRST>
+    static __device__ __forceinline__ void mad_n_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi) {
         const FieldConsts& C = Tag::C();
-        uint32_t t[9];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) t[i] = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint32_t bi = b.v[i];
-            // t += a * bi  (low halves, then high halves)
-            t[0] = mad_lo_cc(a.v[0], bi, t[0]);
-#pragma unroll
-            for (int j = 1; j < 8; ++j) t[j] = madc_lo_cc(a.v[j], bi, t[j]);
-            t[8] = addc(t[8], 0);
-            t[1] = mad_hi_cc(a.v[0], bi, t[1]);
-#pragma unroll
-            for (int j = 1; j < 7; ++j) t[j + 1] = madc_hi_cc(a.v[j], bi, t[j + 1]);
-            t[8] = madc_hi_cc(a.v[7], bi, t[8]);   // cannot carry out: t < 2^288
-            // t = (t + m*p) / 2^32
-            const uint32_t m = t[0] * C.inv;
-            (void)mad_lo_cc(m, C.mod[0], t[0]);
-#pragma unroll
-            for (int j = 1; j < 8; ++j) t[j] = madc_lo_cc(m, C.mod[j], t[j]);
-            t[8] = addc(t[8], 0);
-            t[0] = mad_hi_cc(m, C.mod[0], t[1]);
-#pragma unroll
-            for (int j = 1; j < 7; ++j) t[j] = madc_hi_cc(m, C.mod[j], t[j + 1]);
-            t[7] = madc_hi_cc(m, C.mod[7], t[8]);
-            t[8] = addc(0, 0);
+        if (FIRST) {
+            mul_n(odd, a + 1, bi);
+            mul_n(even, a, bi);
+        } else {
+            asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(even[0]) : "r"(odd[1]));
+            madc_n_rshift(odd, a + 1, bi);
+            cmad_n(even, a, bi);
+            asm volatile("addc.u32 %0, %0, 0;" : "+r"(odd[7]));
         }
-        Fp r;
+        const uint32_t mi = even[0] * C.inv;
+        cmad_n(odd, C.mod + 1, mi);
+        cmad_n(even, C.mod, mi);
+        asm volatile("addc.u32 %0, %0, 0;" : "+r"(odd[7]));
+    }
+    friend __device__ __forceinline__ Fp operator*(const Fp& a, const Fp& b) {
+        uint32_t even[8], odd[8];
+        mad_n_redc<true>(even, odd, a.v, b.v[0]);
+        mad_n_redc<false>(odd, even, a.v, b.v[1]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) r.v[i] = t[i];
+        for (int i = 2; i < 8; i += 2) {
+            mad_n_redc<false>(even, odd, a.v, b.v[i]);
+            mad_n_redc<false>(odd, even, a.v, b.v[i + 1]);
+        }
+        // merge: result limb k = even[k] + odd[k + 1]
+        Fp r;
+        r.v[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int k = 1; k < 7; ++k) r.v[k] = addc_cc(even[k], odd[k + 1]);
+        r.v[7] = addc(even[7], 0);
         r.reduce_once();
         return r;
     }
