@@ -6,8 +6,14 @@ namespace zke { namespace dev { unsigned long long g_kernel_launches = 0; } }
 #include "witness.cu"
 #include "matvec.cu"
 #include "ntt.cu"
-#include "msm.cu"
-#include "fixed_base.cu"
+#include "msm.cuh"
+#include "fixed_base.cuh"
+namespace zke { namespace dev {
+ZKE_DEFINE_CONSTANT_UPLOAD(upload_constants_engine)
+cudaError_t upload_constants_msm_g1(const FieldConsts*, const FieldConsts*);
+cudaError_t upload_constants_msm_g2(const FieldConsts*, const FieldConsts*);
+cudaError_t upload_constants_fixed_base(const FieldConsts*, const FieldConsts*);
+} }
 
 #include "../../include/zkemail_b200.h"
 #include "engine.hpp"
@@ -52,8 +58,10 @@ void select_device(int device) {
     dev::FieldConsts fr, fq;
     fill_consts(fr, fr_params());
     fill_consts(fq, fq_params());
-    CUDA_OK(cudaMemcpyToSymbol(dev::FR_C, &fr, sizeof fr));
-    CUDA_OK(cudaMemcpyToSymbol(dev::FQ_C, &fq, sizeof fq));
+    CUDA_OK(dev::upload_constants_engine(&fr, &fq));
+    CUDA_OK(dev::upload_constants_msm_g1(&fr, &fq));
+    CUDA_OK(dev::upload_constants_msm_g2(&fr, &fq));
+    CUDA_OK(dev::upload_constants_fixed_base(&fr, &fq));
 }
 
 // 32 x 256 window table of multiples of a generator, affine Montgomery, entry d = 0 is infinity

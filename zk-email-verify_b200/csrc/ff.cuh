@@ -17,9 +17,16 @@ struct FieldConsts {
     uint32_t r2[8];   // 2^512 mod p
     uint32_t inv;     // -p^-1 mod 2^32
 };
-// Defined here: all device code is compiled as ONE translation unit (engine.cu includes the kernel files).
-__constant__ FieldConsts FR_C;
-__constant__ FieldConsts FQ_C;
+// One copy per translation unit (whole-program device compilation, no -rdc): every .cu that uses field arithmetic
+// instantiates ZKE_DEFINE_CONSTANT_UPLOAD(name) and the engine calls each TU's upload function once per device.
+static __constant__ FieldConsts FR_C;
+static __constant__ FieldConsts FQ_C;
+#define ZKE_DEFINE_CONSTANT_UPLOAD(fn)                                                          \
+    cudaError_t fn(const ::zke::dev::FieldConsts* fr, const ::zke::dev::FieldConsts* fq) {       \
+        cudaError_t e = cudaMemcpyToSymbol(::zke::dev::FR_C, fr, sizeof(::zke::dev::FieldConsts)); \
+        if (e != cudaSuccess) return e;                                                          \
+        return cudaMemcpyToSymbol(::zke::dev::FQ_C, fq, sizeof(::zke::dev::FieldConsts));          \
+    }
 
 struct FrTag { static __device__ __forceinline__ const FieldConsts& C() { return FR_C; } };
 struct FqTag { static __device__ __forceinline__ const FieldConsts& C() { return FQ_C; } };
@@ -205,14 +212,16 @@ struct Fq2 {
     __device__ __forceinline__ bool operator==(const Fq2& o) const { return c0 == o.c0 && c1 == o.c1; }
     friend __device__ __forceinline__ Fq2 operator+(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; return r; }
     friend __device__ __forceinline__ Fq2 operator-(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; return r; }
-    friend __device__ __forceinline__ Fq2 operator*(const Fq2& a, const Fq2& b) {
+    // not inlined: a G2 addition holds ten of these; inlining them all makes the G2 kernels compile for minutes
+    // and spill (the call costs ~20 instructions against ~600 of work)
+    friend __device__ __noinline__ Fq2 operator*(const Fq2& a, const Fq2& b) {
         Fq t0 = a.c0 * b.c0, t1 = a.c1 * b.c1;
         Fq2 r;
         r.c1 = (a.c0 + a.c1) * (b.c0 + b.c1) - t0 - t1;
         r.c0 = t0 - t1;
         return r;
     }
-    __device__ __forceinline__ Fq2 sqr() const {
+    __device__ __noinline__ Fq2 sqr() const {
         Fq2 r;
         Fq t = c0 * c1;
         r.c0 = (c0 + c1) * (c0 - c1);

@@ -66,3 +66,5 @@ template void fixed_base_batch<Fq2>(const uint8_t*, const uint8_t*, uint32_t, ui
 
 }  // namespace dev
 }  // namespace zke
+
+namespace zke { namespace dev { ZKE_DEFINE_CONSTANT_UPLOAD(upload_constants_fixed_base) } }

@@ -14,6 +14,7 @@
 // (~300 IMAD each) per 64-byte point (SURVEY 8(d) "Which roofline bounds what").
 #include "device_engine.cuh"
 #include "msm.cuh"
+#include <cstdlib>
 
 namespace zke {
 namespace dev {
@@ -134,7 +135,7 @@ __device__ __forceinline__ void for_each_digit(Fr s, const Digits& D, Fn f) {
     }
 }
 
-__global__ void digit_hist_kernel(const uint8_t* __restrict__ scalars, const uint32_t* __restrict__ list,
+static __global__ void digit_hist_kernel(const uint8_t* __restrict__ scalars, const uint32_t* __restrict__ list,
                                   const uint32_t* __restrict__ count_ptr, uint32_t count_fixed, Digits D, uint32_t* hist) {
     const uint32_t count = count_ptr ? *count_ptr : count_fixed;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
@@ -144,7 +145,7 @@ __global__ void digit_hist_kernel(const uint8_t* __restrict__ scalars, const uin
     }
 }
 
-__global__ void digit_scatter_kernel(const uint8_t* __restrict__ scalars, const uint32_t* __restrict__ list,
+static __global__ void digit_scatter_kernel(const uint8_t* __restrict__ scalars, const uint32_t* __restrict__ list,
                                      const uint32_t* __restrict__ count_ptr, uint32_t count_fixed, Digits D,
                                      const uint32_t* __restrict__ offsets, uint32_t* cursor, uint32_t* entries) {
     const uint32_t count = count_ptr ? *count_ptr : count_fixed;
@@ -173,7 +174,7 @@ __device__ __forceinline__ uint32_t scan_f(uint32_t v, uint32_t chunk, uint32_t 
     return v;
 }
 
-__global__ void __launch_bounds__(256) scan_tile_totals_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t chunk, uint32_t levels, uint32_t* tile_sums) {
+static __global__ void __launch_bounds__(256) scan_tile_totals_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t chunk, uint32_t levels, uint32_t* tile_sums) {
     __shared__ uint32_t red[256];
     const uint32_t base = blockIdx.x * SCAN_TILE;
     uint32_t local = 0;
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(256) scan_tile_totals_kernel(const uint32_t* _
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = red[0];
 }
 // exclusive scan of up to 1024 * 8 values in one block (in place)
-__global__ void __launch_bounds__(1024) scan_small_kernel(uint32_t* data, uint32_t n, uint32_t* total_out) {
+static __global__ void __launch_bounds__(1024) scan_small_kernel(uint32_t* data, uint32_t n, uint32_t* total_out) {
     __shared__ uint32_t sums[1024];
     const uint32_t tid = threadIdx.x;
     const uint32_t per = (n + 1023) / 1024;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(1024) scan_small_kernel(uint32_t* data, uint32
     for (uint32_t i = beg; i < end; ++i) { uint32_t v = data[i]; data[i] = run; run += v; }
     if (tid == 1023 && total_out) *total_out = sums[1023];
 }
-__global__ void __launch_bounds__(256) scan_tile_apply_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t chunk, uint32_t levels,
+static __global__ void __launch_bounds__(256) scan_tile_apply_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t chunk, uint32_t levels,
                                                               const uint32_t* __restrict__ tile_base, uint32_t* out) {
     __shared__ uint32_t sums[256];
     const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 8;
@@ -231,7 +232,7 @@ static void exclusive_scan(const uint32_t* in, uint32_t n, uint32_t chunk, uint3
     ZKE_COUNT_LAUNCH(3);
 }
 
-__global__ void fill_work_kernel(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off, uint32_t n_buckets,
+static __global__ void fill_work_kernel(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off, uint32_t n_buckets,
                                  uint32_t CHUNK, uint32_t levels, uint32_t* work_bucket) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_buckets) return;
@@ -240,8 +241,8 @@ __global__ void fill_work_kernel(const uint32_t* __restrict__ hist, const uint32
 }
 
 // one thread per chunk: partial[w] = sum of (+/-) points of the chunk
-template <class F>
-__global__ void __launch_bounds__(128)
+template <class F, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 chunk_sum_kernel(const uint8_t* __restrict__ points, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
                  const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off, const uint32_t* __restrict__ work_bucket,
                  uint32_t n_buckets, uint32_t CHUNK, uint8_t* partial) {
@@ -337,6 +338,7 @@ __global__ void gather_windows_kernel(const uint8_t* __restrict__ group_out, uin
 }
 
 // ---------------------------------------------------------------- host orchestration
+#if defined(ZKE_MSM_G1)
 MsmConfig msm_config_witness() { MsmConfig c; c.c = 8; c.chunk = 32; c.group = 8; c.classify = true; c.extra_passes = 2; return c; }
 MsmConfig msm_config_full(uint32_t n) {
     MsmConfig c;
@@ -344,6 +346,7 @@ MsmConfig msm_config_full(uint32_t n) {
     c.chunk = 256; c.group = 16; c.classify = false; c.extra_passes = 0;
     return c;
 }
+#endif
 
 template <class F>
 size_t MsmPlan<F>::workspace_bytes(uint32_t n, const MsmConfig& cfg) {
@@ -449,7 +452,15 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     exclusive_scan(hist, n_buckets, D.chunk, 0, chunk_off, tiles, st);
     fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, chunk_off, n_buckets, D.chunk, 0, work_bucket);
     if (ev) cudaEventRecord(ev[0], st);
-    chunk_sum_kernel<F><<<148 * 16, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
+    {
+        // blocks per SM the bucket kernel is compiled for (register cap 128 / 96 / 80): more resident warps hide the
+        // IMAD.WIDE carry-chain latency; tunable for experiments with ZKE_CHUNK_MINB
+        static int minb = -1;
+        if (minb < 0) { const char* e = getenv("ZKE_CHUNK_MINB"); minb = e ? atoi(e) : (sizeof(F) == 32 ? 5 : 4); }
+        if (minb >= 6) chunk_sum_kernel<F, 6><<<148 * 6 * 4, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
+        else if (minb == 5) chunk_sum_kernel<F, 5><<<148 * 5 * 4, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
+        else chunk_sum_kernel<F, 4><<<148 * 4 * 4, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
+    }
     if (ev) cudaEventRecord(ev[1], st);
     // extra passes over the per-chunk partial sums
     uint8_t *items = partial, *items_next = partial2;
@@ -470,8 +481,13 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     ZKE_COUNT_LAUNCH(7);
 }
 
+#if defined(ZKE_MSM_G1)
 template struct MsmPlan<Fq>;
+#elif defined(ZKE_MSM_G2)
 template struct MsmPlan<Fq2>;
+#else
+#error "compile msm.cu through msm_g1.cu / msm_g2.cu"
+#endif
 
 }  // namespace dev
 }  // namespace zke

@@ -17,15 +17,31 @@
 namespace zke {
 namespace dev {
 
+__device__ __forceinline__ Fr lc_term(const DevProgram& P, const Fr& acc, const uint2& term, const Fr& x) {
+    if (term.y == 0) return acc + x;
+    if (term.y == 1) return acc - x;
+    return acc + Fr::load(P.coef_r + 32ull * term.y) * x;   // (c*R) (x) -> c*x, standard form
+}
+
+// sum of coef * w over the LC's terms.  Terms are fetched four at a time: the four descriptor loads and then the four
+// witness loads are independent of each other, so a thread has up to four gathers in flight instead of one dependent
+// load after another (the level time of the witness program is the latency of its longest LC).
 __device__ __forceinline__ Fr eval_lc(const DevProgram& P, const uint8_t* w, uint32_t id) {
     Fr acc = Fr::zero();
-    const uint32_t beg = P.lc_ptr[id], end = P.lc_ptr[id + 1];
-    for (uint32_t k = beg; k < end; ++k) {
-        const uint2 term = P.lc_terms[k];
-        Fr x = Fr::load(w + 32ull * term.x);
-        if (term.y == 0) acc = acc + x;
-        else if (term.y == 1) acc = acc - x;
-        else acc = acc + Fr::load(P.coef_r + 32ull * term.y) * x;   // (c*R) (x) -> c*x, standard form
+    uint32_t k = P.lc_ptr[id];
+    const uint32_t end = P.lc_ptr[id + 1];
+    for (; k + 4 <= end; k += 4) {
+        const uint2 t0 = P.lc_terms[k], t1 = P.lc_terms[k + 1], t2 = P.lc_terms[k + 2], t3 = P.lc_terms[k + 3];
+        const Fr x0 = Fr::load(w + 32ull * t0.x), x1 = Fr::load(w + 32ull * t1.x);
+        const Fr x2 = Fr::load(w + 32ull * t2.x), x3 = Fr::load(w + 32ull * t3.x);
+        acc = lc_term(P, acc, t0, x0);
+        acc = lc_term(P, acc, t1, x1);
+        acc = lc_term(P, acc, t2, x2);
+        acc = lc_term(P, acc, t3, x3);
+    }
+    for (; k < end; ++k) {
+        const uint2 t = P.lc_terms[k];
+        acc = lc_term(P, acc, t, Fr::load(w + 32ull * t.x));
     }
     return acc;
 }
