@@ -129,7 +129,7 @@ enum {
     ZKE_STAGE_MSM_B2 = 8,
     ZKE_N_STAGES = 9
 };
-/* Number of concurrent proving lanes (streams) used by zke_prove, 1..allocated (default min(4, max_batch), or the
+/* Number of concurrent proving lanes (streams) used by zke_prove, 1..allocated (default min(8, max_batch), or the
  * ZKE_LANES environment variable at zke_ctx_open).  Returns the value in effect.  Profiling forces one lane. */
 int zke_ctx_set_lanes(zke_ctx* x, int n);
 int zke_ctx_profile(zke_ctx* x, int enable);                       /* enabling also clears the accumulators */

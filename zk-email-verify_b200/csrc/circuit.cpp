@@ -318,6 +318,21 @@ Circuit Builder::finalize() {
         c.level_ptr.swap(lp);
     }
     c.ops.swap(sorted);
+    // Within a level the ops are independent: order them by opcode and by the amount of work (LC terms) so that the
+    // 32 lanes of a warp of the device interpreter execute the same case with similar trip counts.
+    auto op_cost = [&](const WOp& o) -> uint32_t {
+        auto len = [&](uint32_t id) { return c.lc_ptr[id + 1] - c.lc_ptr[id]; };
+        if (o.code == OP_LIN) return len(o.a);
+        if (o.code == OP_QUAD) return len(o.a) + len(o.b) + len(o.c);
+        return 0;
+    };
+    for (uint32_t l = 0; l + 1 < c.level_ptr.size(); ++l) {
+        auto beg = c.ops.begin() + c.level_ptr[l], end = c.ops.begin() + c.level_ptr[l + 1];
+        std::stable_sort(beg, end, [&](const WOp& x, const WOp& y) {
+            if (x.code != y.code) return x.code < y.code;
+            return op_cost(x) < op_cost(y);
+        });
+    }
     return std::move(c_);
 }
 

@@ -98,7 +98,9 @@ struct zke_zkey {
     G1AffineH alpha1, beta1, delta1;
     G2AffineH beta2, gamma2, delta2;
     std::vector<G1AffineH> ic;
-    DevBuf A, B1, B2, C, H;   // affine Montgomery points on the device
+    DevBuf A, B1, B2, C, H;   // affine Montgomery points on the device; H holds h_levels window levels [level][N]
+    int h_levels = 1;         // > 1: level j = 2^(c j) * H (fixed-base table for the H multi-exponentiation)
+    dev::MsmConfig cfg_h;
 };
 
 struct zke_ctx {
@@ -195,7 +197,29 @@ static zke_zkey* do_setup(const zke_circuit* zc, uint64_t seed, int device) {
     run_g1(S.a, zk->A);
     run_g1(S.b, zk->B1);
     run_g1(S.kc, zk->C);
-    run_g1(S.h, zk->H);
+    {
+        // H points, then (unless ZKE_H_PRECOMP=0) the fixed-base table levels 2^(c j) * H_i
+        const char* e = getenv("ZKE_H_PRECOMP");
+        const bool precomp = !(e && atoi(e) == 0);
+        zk->cfg_h = dev::msm_config_full((uint32_t)N, precomp);
+        zk->h_levels = precomp ? dev::msm_windows(zk->cfg_h) : 1;
+        std::vector<U256> std_s = to_standard(S.h);
+        scal.upload(std_s);
+        zk->H.alloc((size_t)zk->h_levels * N * sizeof(dev::G1Affine));
+        for (size_t off = 0; off < N; off += SLAB) {
+            uint32_t cnt = (uint32_t)std::min<size_t>(SLAB, N - off);
+            dev::fixed_base_batch<dev::Fq>(t1.p, scal.p + 32 * off, cnt, scratch.p, zk->H.p + sizeof(dev::G1Affine) * off, st);
+        }
+        for (int lvl = 1; lvl < zk->h_levels; ++lvl) {
+            const uint8_t* prev = zk->H.p + (size_t)(lvl - 1) * N * sizeof(dev::G1Affine);
+            uint8_t* cur = zk->H.p + (size_t)lvl * N * sizeof(dev::G1Affine);
+            for (size_t off = 0; off < N; off += SLAB) {
+                uint32_t cnt = (uint32_t)std::min<size_t>(SLAB, N - off);
+                dev::scale_pow2_batch<dev::Fq>(prev + sizeof(dev::G1Affine) * off, cnt, zk->cfg_h.c, scratch.p, cur + sizeof(dev::G1Affine) * off, st);
+            }
+        }
+        CUDA_OK(cudaStreamSynchronize(st));
+    }
     {
         std::vector<U256> std_s = to_standard(S.b);
         scal.upload(std_s);
@@ -317,11 +341,11 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         x->tw_fwd.upload(fw); x->tw_inv.upload(iv); x->coset_scale.upload(cs);
         x->ntt.tw_fwd = x->tw_fwd.p; x->ntt.tw_inv = x->tw_inv.p; x->ntt.log_n = (int)log_n;
         x->cfg_w = dev::msm_config_witness();
-        x->cfg_h = dev::msm_config_full((uint32_t)N);
+        x->cfg_h = zk->cfg_h;
         size_t ws = std::max(dev::MsmPlan<dev::Fq>::workspace_bytes(c.n_vars, x->cfg_w),
                              dev::MsmPlan<dev::Fq>::workspace_bytes((uint32_t)N, x->cfg_h));
         ws = std::max(ws, dev::MsmPlan<dev::Fq2>::workspace_bytes(c.n_vars, x->cfg_w));
-        int want = 4;
+        int want = 8;
         if (const char* e = getenv("ZKE_LANES")) want = atoi(e);
         want = std::max(1, std::min(ZKE_MAX_LANES, std::min<int>(want, (int)max_batch)));
         for (int i = 0; i < want; ++i) {
@@ -396,7 +420,7 @@ static void write_fq(uint8_t* dst, const Fq& x) { U256 s = x.to_u256(); memcpy(d
 template <class F>
 static AffineH<F> finish_msm(const uint8_t* block, const dev::MsmConfig& cfg) {
     const XyzzH<F>* slots = reinterpret_cast<const XyzzH<F>*>(block);
-    const int n_windows = (255 + cfg.c - 1) / cfg.c;
+    const int n_windows = cfg.precomputed ? 1 : (255 + cfg.c - 1) / cfg.c;   // precomputed tables: one bucket set, no Horner
     XyzzH<F> acc = XyzzH<F>::inf();
     for (int j = n_windows - 1; j >= 0; --j) {
         if (!acc.is_inf()) for (int k = 0; k < cfg.c; ++k) acc.dbl();

@@ -53,6 +53,27 @@ xyzz_to_affine_kernel(const uint8_t* __restrict__ in_xyzz, uint32_t n, uint8_t* 
     }
 }
 
+// out[i] = 2^k * in[i]  (affine in, XYZZ out)
+template <class F>
+__global__ void __launch_bounds__(128)
+scale_pow2_kernel(const uint8_t* __restrict__ in_affine, uint32_t n, int k, uint8_t* out_xyzz) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XYZZ<F> p = XYZZ<F>::from_affine(Affine<F>::load(in_affine + sizeof(Affine<F>) * (size_t)i));
+    for (int j = 0; j < k; ++j) p.dbl();
+    p.store(out_xyzz + sizeof(XYZZ<F>) * (size_t)i);
+}
+
+template <class F>
+void scale_pow2_batch(const uint8_t* in_affine, uint32_t n, int k, uint8_t* scratch_xyzz, uint8_t* out_affine, cudaStream_t st) {
+    if (!n) return;
+    scale_pow2_kernel<F><<<(n + 127) / 128, 128, 0, st>>>(in_affine, n, k, scratch_xyzz);
+    const uint32_t threads = (n + TO_AFFINE_BATCH - 1) / TO_AFFINE_BATCH;
+    xyzz_to_affine_kernel<F><<<(threads + 127) / 128, 128, 0, st>>>(scratch_xyzz, n, out_affine);
+    ZKE_COUNT_LAUNCH(2);
+}
+template void scale_pow2_batch<Fq>(const uint8_t*, uint32_t, int, uint8_t*, uint8_t*, cudaStream_t);
+
 template <class F>
 void fixed_base_batch(const uint8_t* table, const uint8_t* scalars, uint32_t n, uint8_t* scratch_xyzz, uint8_t* out_affine, cudaStream_t st) {
     if (!n) return;

@@ -87,6 +87,8 @@ struct Digits {
     uint32_t half;   // 2^(c-1) buckets per window
     uint32_t chunk;  // max bucket entries accumulated by one thread
     uint32_t group;  // buckets per running-sum thread
+    uint32_t window_bucket_stride;  // half, or 0 when all windows share one bucket set (precomputed tables)
+    uint32_t window_point_stride;   // 0, or n when window j uses table level j
 };
 
 __device__ __forceinline__ uint32_t window_bits(const Fr& s, int bit, int c) {
@@ -141,7 +143,7 @@ static __global__ void digit_hist_kernel(const uint8_t* __restrict__ scalars, co
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < count; t += gridDim.x * blockDim.x) {
         const uint32_t idx = list ? list[t] : t;
         Fr s = load_scalar(scalars, idx);
-        for_each_digit(s, D, [&](int j, uint32_t b, bool) { atomicAdd(&hist[(uint32_t)j * D.half + b], 1u); });
+        for_each_digit(s, D, [&](int j, uint32_t b, bool) { atomicAdd(&hist[(uint32_t)j * D.window_bucket_stride + b], 1u); });
     }
 }
 
@@ -153,9 +155,9 @@ static __global__ void digit_scatter_kernel(const uint8_t* __restrict__ scalars,
         const uint32_t idx = list ? list[t] : t;
         Fr s = load_scalar(scalars, idx);
         for_each_digit(s, D, [&](int j, uint32_t b, bool neg) {
-            const uint32_t bucket = (uint32_t)j * D.half + b;
+            const uint32_t bucket = (uint32_t)j * D.window_bucket_stride + b;
             const uint32_t pos = offsets[bucket] + atomicAdd(&cursor[bucket], 1u);
-            entries[pos] = idx | (neg ? 0x80000000u : 0u);
+            entries[pos] = ((uint32_t)j * D.window_point_stride + idx) | (neg ? 0x80000000u : 0u);
         });
     }
 }
@@ -340,10 +342,16 @@ __global__ void gather_windows_kernel(const uint8_t* __restrict__ group_out, uin
 // ---------------------------------------------------------------- host orchestration
 #if defined(ZKE_MSM_G1)
 MsmConfig msm_config_witness() { MsmConfig c; c.c = 8; c.chunk = 32; c.group = 8; c.classify = true; c.extra_passes = 2; return c; }
-MsmConfig msm_config_full(uint32_t n) {
+MsmConfig msm_config_full(uint32_t n, bool precomputed) {
     MsmConfig c;
     c.c = n >= (1u << 18) ? 16 : (n >= (1u << 12) ? 12 : 8);
     c.chunk = 256; c.group = 16; c.classify = false; c.extra_passes = 0;
+    c.precomputed = precomputed;
+    if (precomputed) {
+        // one shared bucket set of 2^(c-1) buckets: pick c so that the buckets (~ n * W / 2^(c-1) entries each) still
+        // number in the hundreds of thousands for parallelism; 13 table levels at 2^22 points (3.5 GB)
+        c.c = n >= (1u << 20) ? 20 : (n >= (1u << 16) ? 17 : (n >= (1u << 10) ? 12 : 8));
+    }
     return c;
 }
 #endif
@@ -352,10 +360,11 @@ template <class F>
 size_t MsmPlan<F>::workspace_bytes(uint32_t n, const MsmConfig& cfg) {
     const int W = (255 + cfg.c - 1) / cfg.c;
     const size_t half = (size_t)1 << (cfg.c - 1);
-    const size_t n_buckets = half * W;
+    const size_t bucket_sets = cfg.precomputed ? 1 : W;
+    const size_t n_buckets = half * bucket_sets;
     const size_t max_entries = (size_t)n * W;
     const size_t max_chunks = n_buckets + max_entries / cfg.chunk + 1;
-    const size_t groups = ((half + cfg.group - 1) / cfg.group) * W;
+    const size_t groups = ((half + cfg.group - 1) / cfg.group) * bucket_sets;
     size_t b = 0;
     auto al = [&](size_t x) { b += (x + 255) & ~(size_t)255; };
     al(4 * 2);                         // counters
@@ -385,12 +394,15 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     D.half = 1u << (cfg.c - 1);
     D.chunk = cfg.chunk;
     D.group = cfg.group;
+    D.window_bucket_stride = cfg.precomputed ? 0 : D.half;
+    D.window_point_stride = cfg.precomputed ? n : 0;
     if (D.n_windows > MSM_MAX_WINDOWS) return;
-    const uint32_t n_buckets = D.half * D.n_windows;
+    const uint32_t bucket_sets = cfg.precomputed ? 1 : (uint32_t)D.n_windows;
+    const uint32_t n_buckets = D.half * bucket_sets;
     const size_t max_entries = (size_t)n * D.n_windows;
     const size_t max_chunks = n_buckets + max_entries / cfg.chunk + 1;
     const uint32_t groups_per_window = (D.half + D.group - 1) / D.group;
-    const uint32_t groups = groups_per_window * D.n_windows;
+    const uint32_t groups = groups_per_window * bucket_sets;
     uint8_t* p = ws;
     auto take = [&](size_t x) { uint8_t* r = p; p += (x + 255) & ~(size_t)255; return r; };
     uint32_t* counters = (uint32_t*)take(8);
@@ -476,8 +488,8 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
         ++levels;
     }
     group_sum_kernel<F><<<(groups + 127) / 128, 128, 0, st>>>(items, hist, off_cur, D.half, groups, D.chunk, levels, D.group, group_out);
-    window_reduce_kernel<F><<<D.n_windows, 512, 0, st>>>(group_out, groups_per_window);
-    gather_windows_kernel<F><<<1, 64, 0, st>>>(group_out, groups_per_window, D.n_windows, res_windows);
+    window_reduce_kernel<F><<<bucket_sets, 512, 0, st>>>(group_out, groups_per_window);
+    gather_windows_kernel<F><<<1, 64, 0, st>>>(group_out, groups_per_window, bucket_sets, res_windows);
     ZKE_COUNT_LAUNCH(7);
 }
 

@@ -10,9 +10,14 @@ struct MsmConfig {
     uint32_t group = 16;   // buckets per running-sum thread
     bool classify = false; // true: drop zero scalars / infinite points and sum unit scalars outside the buckets
     uint32_t extra_passes = 0;  // further fan-in-32 reductions of the per-chunk partial sums (skewed buckets)
+    // true: `points` is a table [n_windows][n] with level j holding 2^(c j) * P_i (fixed-base precomputation, legal
+    // because the proving key is reused for every proof): all windows then share ONE bucket set, so the window
+    // count no longer multiplies the bucket count, c can grow (fewer additions per point) and no Horner tail is left
+    bool precomputed = false;
 };
 MsmConfig msm_config_witness();          // witness-scalar MSMs (mostly 0 / 1 / byte-sized scalars)
-MsmConfig msm_config_full(uint32_t n);   // full-width scalars (the H MSM)
+MsmConfig msm_config_full(uint32_t n, bool precomputed);   // full-width scalars (the H MSM)
+inline int msm_windows(const MsmConfig& c) { return (255 + c.c - 1) / c.c; }
 
 // Result block of one MSM (device or host memory), XYZZ points:
 //   slots [0, MSM_ONES_SLOTS)                 partial sums of the unit-scalar points (infinity-padded)
