@@ -115,3 +115,15 @@ def poseidon_large(value: int, num_chunks: int, bits_per_chunk: int) -> int:
     (/root/reference/packages/helpers/src/hash.ts:17-25): chunk little-endian, hash once."""
     mask = (1 << bits_per_chunk) - 1
     return poseidon([(value >> (i * bits_per_chunk)) & mask for i in range(num_chunks)])
+
+
+def poseidon_modular(inputs) -> int:
+    """helpers ``poseidonModular(inputs)`` (/root/reference/packages/helpers/src/hash.ts:27-59): hash chunks of 16,
+    fold the chunk hashes left to right with Poseidon(2)."""
+    if not inputs:
+        raise ValueError("No inputs provided")
+    out = None
+    for start in range(0, len(inputs), 16):
+        h = poseidon(inputs[start:start + 16])
+        out = h if out is None else poseidon([out, h])
+    return out

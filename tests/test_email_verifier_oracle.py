@@ -84,3 +84,44 @@ def test_rejects_wrong_body_hash_index(setup):  # :165-186
     bad["bodyHashIndex"] = str(int(bad["bodyHashIndex"]) + 1)
     with pytest.raises(AssertFailed):
         oracle_witness(c, bad)
+
+
+# ---- circuit variants: email-verifier-no-body.test.ts:34-47, -with-header-mask, -with-body-mask.test.ts:33-58 ----------
+def _synthetic(maxh=640, maxb=768, **extra):
+    key = synthetic.generate_key()
+    email = synthetic.make_signed_email(2, key, body_len=300)
+    dk = verify_dkim_signature(email, resolver=lambda n, t: [synthetic.key_record(key)])
+    params = {"maxHeadersLength": maxh, "maxBodyLength": maxb}
+    params.update(extra)
+    return dk, generate_email_verifier_inputs_from_dkim_result(dk, params)
+
+
+def test_no_body_variant():
+    c = Circuit("EmailVerifier", [640, 768, 121, 17, 1, 0, 0, 0, 1])
+    dk, inputs = _synthetic(ignoreBodyHashCheck=True)
+    assert "emailBody" not in inputs
+    w = oracle_witness(c, inputs)
+    digest = hashlib.sha256(dk.headers).digest()
+    assert_out(w, {"shaHi": int.from_bytes(digest[:16], "big"), "shaLo": int.from_bytes(digest[16:], "big")})
+
+
+def test_header_mask_variant():
+    c = Circuit("EmailVerifier", [640, 768, 121, 17, 0, 1, 0, 0, 1])
+    mask = [1 if i % 3 == 0 else 0 for i in range(640)]
+    dk, inputs = _synthetic(enableHeaderMasking=True, headerMask=mask)
+    w = oracle_witness(c, inputs)
+    hdr = [int(x) for x in inputs["emailHeader"]]
+    assert_out(w, {"maskedHeader": [h * m for h, m in zip(hdr, mask)]})
+    bad = dict(inputs)
+    bad["headerMask"] = [2] + mask[1:]              # AssertBit
+    with pytest.raises(AssertFailed):
+        oracle_witness(c, bad)
+
+
+def test_body_mask_variant():
+    c = Circuit("EmailVerifier", [640, 768, 121, 17, 0, 0, 1, 0, 1])
+    mask = [1] * 10 + [0] * 758
+    dk, inputs = _synthetic(enableBodyMasking=True, bodyMask=mask)
+    w = oracle_witness(c, inputs)
+    body = [int(x) for x in inputs["emailBody"]]
+    assert_out(w, {"maskedBody": body[:10] + [0] * 758})

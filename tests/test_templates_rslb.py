@@ -1,0 +1,55 @@
+"""RemoveSoftLineBreaks(32) and PoseidonModular(37): the cases of
+/root/reference/packages/circuits/tests/remove-soft-line-breaks.test.ts (golden vectors extracted by
+tests/golden/scripts/extract_rslb_vectors.py) and poseidon-modular.test.ts:24-36 (circuit output == helper value)."""
+import json
+import os
+import random
+import pytest
+from zkemail_b200 import Circuit
+from zkutil import oracle_witness, assert_out, AssertFailed
+from oracle import poseidon as op
+
+CASES = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "remove_soft_line_breaks.json")))
+
+
+@pytest.fixture(scope="module")
+def rslb():
+    return Circuit("RemoveSoftLineBreaks", [32])
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_remove_soft_line_breaks(rslb, case):
+    assert len(CASES) == 7
+    w = oracle_witness(rslb, {"encoded": case["encoded"], "decoded": case["decoded"]})
+    assert_out(w, {"isValid": case["isValid"]})
+
+
+def test_poseidon_modular_37():
+    c = Circuit("PoseidonModular", [37])
+    rnd = random.Random(2024)
+    inputs = [rnd.randrange(1 << 53) for _ in range(37)]
+    w = oracle_witness(c, {"in": inputs})
+    assert w[1] == op.poseidon_modular(inputs)      # poseidon-modular.test.ts:35 reads witness[1]
+
+
+def test_email_verifier_with_soft_line_breaks():
+    """email-verifier-with-soft-line-breaks.test.ts scenario on a synthetic email whose body carries '=\\r\\n' breaks."""
+    import zkemail_b200 as z
+    c = Circuit("EmailVerifier", [640, 768, 121, 17, 0, 0, 0, 1, 1])
+    key = z.synthetic.generate_key()
+    body = b"This is a quoted-printable body with a soft line =\r\nbreak in the middle and another one right he=\r\nre.\r\n"
+    email = z.synthetic.make_signed_email(9, key, body_len=len(body))
+    # replace the synthetic body: rebuild a signed email with our body
+    from zkemail_b200.synthetic import make_signed_email
+    email = make_signed_email(9, key, body_len=len(body), body_override=body)
+    dk = z.verify_dkim_signature(email, resolver=lambda n, t: [z.synthetic.key_record(key)])
+    inputs = z.generate_email_verifier_inputs_from_dkim_result(
+        dk, {"maxHeadersLength": 640, "maxBodyLength": 768, "removeSoftLineBreaks": True})
+    assert "decodedEmailBodyIn" in inputs
+    oracle_witness(c, inputs)
+    bad = dict(inputs)
+    dec = list(bad["decodedEmailBodyIn"])
+    dec[3] = str((int(dec[3]) + 1) % 128)
+    bad["decodedEmailBodyIn"] = dec
+    with pytest.raises(AssertFailed):
+        oracle_witness(c, bad)

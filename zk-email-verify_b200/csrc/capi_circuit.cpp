@@ -131,6 +131,16 @@ Circuit build_named(const std::string& name, const std::vector<int64_t>& p) {
         auto out = b.declare_outputs("out", 1);
         LCVec in = inputs(b, "inputs", (uint32_t)p[0]);
         outputs(b, "out", {poseidon(b, in)}, out);
+    } else if (name == "PoseidonModular") {   // test-circuits/poseidon-modular-test.circom
+        need(1);
+        auto out = b.declare_outputs("out", 1);
+        LCVec in = inputs(b, "in", (uint32_t)p[0]);
+        outputs(b, "out", {poseidon_modular(b, in)}, out);
+    } else if (name == "RemoveSoftLineBreaks") {   // test-circuits/remove-soft-line-breaks-test.circom
+        need(1);
+        auto out = b.declare_outputs("isValid", 1);
+        LCVec enc = inputs(b, "encoded", (uint32_t)p[0]), dec = inputs(b, "decoded", (uint32_t)p[0]);
+        outputs(b, "isValid", {remove_soft_line_breaks(b, enc, dec)}, out);
     } else if (name == "ItemAtIndex") {
         need(1);
         auto out = b.declare_outputs("out", 1);

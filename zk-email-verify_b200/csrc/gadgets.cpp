@@ -1,4 +1,5 @@
 #include "gadgets.hpp"
+#include <algorithm>
 #include <stdexcept>
 
 namespace zke {
@@ -621,6 +622,60 @@ LC poseidon_large(Builder& b, uint32_t bits_per_chunk, const LCVec& in) {
     return poseidon(b, pin);
 }
 
+LC poseidon_modular(Builder& b, const LCVec& in) {
+    ScopeGuard g(b, "PoseidonModular");
+    const size_t n = in.size();
+    if (n == 0) throw std::runtime_error("PoseidonModular: no inputs");
+    LC out;
+    for (size_t start = 0, i = 0; start < n; start += 16, ++i) {
+        const size_t end = std::min(n, start + 16);
+        LC chunk_hash = poseidon(b, LCVec(in.begin() + start, in.begin() + end));   // Slice + Poseidon(16 | last_chunk_size)
+        out = (i == 0) ? chunk_hash : poseidon(b, {out, chunk_hash});                // _out = Poseidon(2)([_out, chunk_hash])
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------- helpers/remove-soft-line-breaks.circom
+LC remove_soft_line_breaks(Builder& b, const LCVec& encoded, const LCVec& decoded) {
+    ScopeGuard g(b, "RemoveSoftLineBreaks");
+    const size_t L = encoded.size();
+    if (decoded.size() != L || L < 3) throw std::runtime_error("RemoveSoftLineBreaks: bad lengths");
+    LCVec hin(encoded);
+    hin.insert(hin.end(), decoded.begin(), decoded.end());
+    LC r = poseidon_modular(b, hin);                                     // r <== rHasher.out
+    LCVec is_eq(L), is_cr(L), is_lf(L), soft(L), should_zero(L), processed(L);
+    for (size_t i = 0; i < L; ++i) is_eq[i] = is_equal(b, encoded[i], const_u64(61));
+    for (size_t i = 0; i + 1 < L; ++i) is_cr[i] = is_equal(b, encoded[i + 1], const_u64(13));
+    for (size_t i = 0; i + 2 < L; ++i) is_lf[i] = is_equal(b, encoded[i + 2], const_u64(10));
+    for (size_t i = 0; i + 2 < L; ++i) {
+        LC t = b.mul(is_eq[i], is_cr[i]);                                // tempSoftBreak
+        soft[i] = b.mul(t, is_lf[i]);                                    // isSoftBreak
+    }
+    for (size_t i = 0; i < L; ++i) {
+        LC e;
+        if (i == 0) e = soft[0];
+        else if (i == 1) e = soft[1] + soft[0];
+        else if (i == L - 1) e = soft[i - 1] + soft[i - 2];
+        else e = soft[i] + soft[i - 1] + soft[i - 2];
+        should_zero[i] = b.signal(e);
+        processed[i] = b.mul(one_lc() - should_zero[i], encoded[i]);     // (1 - shouldZero) * encoded
+    }
+    // powers of r: Mux1 out = (c1 - c0) * s + c0
+    LCVec r_enc(L), r_dec(L);
+    r_enc[0] = b.mul_add(one_lc() - r, should_zero[0], r);
+    for (size_t i = 1; i < L; ++i) {
+        LC c0 = b.mul(r_enc[i - 1], r);                                  // muxEnc[i].c[0] <== rEnc[i-1] * r
+        r_enc[i] = b.mul_add(r_enc[i - 1] - c0, should_zero[i], c0);
+    }
+    r_dec[0] = r;
+    for (size_t i = 1; i < L; ++i) r_dec[i] = b.mul(r_dec[i - 1], r);
+    LC sum_enc = b.mul(r_enc[0], processed[0]);
+    for (size_t i = 1; i < L; ++i) sum_enc = b.mul_add(r_enc[i], processed[i], sum_enc);
+    LC sum_dec = b.mul(r_dec[0], decoded[0]);
+    for (size_t i = 1; i < L; ++i) sum_dec = b.mul_add(r_dec[i], decoded[i], sum_dec);
+    return is_equal(b, sum_enc, sum_dec);                                // isValid
+}
+
 // ---------------------------------------------------------------- email-verifier.circom
 Circuit build_email_verifier(const EmailVerifierParams& P, bool materialize_linear) {
     const uint32_t H = P.max_headers_length, Bd = P.max_body_length, n = P.n, k = P.k;
@@ -695,8 +750,10 @@ Circuit build_email_verifier(const EmailVerifierParams& P, bool materialize_line
             for (int j = 0; j < 8; ++j) bits[7 - j] = computed[i * 8 + j];
             b.enforce_eq(bits2num(b, bits), header_body_hash[i]);
         }
-        if (P.remove_soft_line_breaks)
-            throw std::runtime_error("removeSoftLineBreaks=1 is not built yet (SURVEY 8(f) rank 3)");
+        if (P.remove_soft_line_breaks) {                                 // :148-156
+            LC valid = remove_soft_line_breaks(b, email_body, decoded_in);
+            b.enforce_eq(valid, one_lc());                               // qpEncodingChecker.isValid === 1
+        }
         if (P.enable_body_masking) {                                     // :158-166
             LCVec m = byte_mask(b, email_body, body_mask);
             for (uint32_t i = 0; i < Bd; ++i) b.assign_output(masked_body[i], m[i]);

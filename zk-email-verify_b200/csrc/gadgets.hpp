@@ -42,6 +42,8 @@ LCVec pack_bits(Builder& b, const LCVec& in, uint32_t bits_per_element);    // u
 LCVec byte_mask(Builder& b, const LCVec& in, const LCVec& mask);            // utils/bytes.circom:173-185
 LCVec select_regex_reveal(Builder& b, const LCVec& in, const LC& start_index, uint32_t max_reveal_len);  // utils/regex.circom:17-52
 LC poseidon_large(Builder& b, uint32_t bits_per_chunk, const LCVec& in);    // utils/hash.circom:15-39
+LC poseidon_modular(Builder& b, const LCVec& in);                           // utils/hash.circom:49-83
+LC remove_soft_line_breaks(Builder& b, const LCVec& encoded, const LCVec& decoded);   // helpers/remove-soft-line-breaks.circom:14-126 (returns isValid)
 
 // ---- lib/ ------------------------------------------------------------------------------------
 LCVec sha256_general(Builder& b, const LCVec& padded_in_bits, const LC& padded_in_length_bits,

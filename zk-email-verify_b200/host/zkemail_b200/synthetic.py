@@ -42,8 +42,8 @@ def synthetic_body(index: int, length: int = 1024, marker: str | None = None) ->
 
 
 def make_signed_email(index: int, key, body_len: int = 1024, domain: str = "example.com", selector: str = "sel",
-                      marker: str | None = None) -> bytes:
-    body = synthetic_body(index, body_len, marker)
+                      marker: str | None = None, body_override: bytes | None = None) -> bytes:
+    body = body_override if body_override is not None else synthetic_body(index, body_len, marker)
     headers = [
         b"from: sender%04d@%s" % (index, domain.encode()),
         b"Content-Type: text/plain; charset=us-ascii",
