@@ -86,6 +86,113 @@ ntt_pass_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, cons
     }
 }
 
+// ---- fast path: tile of 1024 elements, stage count K and addressing mode known at compile time ------------------
+// Shared memory holds the tile as two planes of uint4 (limbs 0-3 / limbs 4-7): a quarter-warp reading consecutive
+// elements touches 128 contiguous bytes per plane, so the 128-bit shared loads are conflict-free.  All index
+// arithmetic is shifts and masks; the twiddle of the next stage is fetched before the current stage's product so
+// the L2 latency of the table lookup overlaps the multiplication.
+template <bool DIF, int K, bool STRIDED>
+__global__ void __launch_bounds__(512)
+ntt_pass_fast_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, const uint8_t* __restrict__ scale,
+                     int log_n, int s_lo) {
+    constexpr int TILE_LOG = 10, TILE = 1 << TILE_LOG, J = 1 << K, L_LOG = TILE_LOG - K, L = 1 << L_LOG;
+    __shared__ uint4 plane0[TILE], plane1[TILE];
+    const int s_hi = s_lo + K - 1;
+    const uint32_t bid = blockIdx.x;
+    uint32_t hi = 0, lo_base = 0;
+    if (STRIDED) {
+        const uint32_t lo_blocks_log = s_lo - L_LOG;
+        lo_base = (bid & ((1u << lo_blocks_log) - 1)) << L_LOG;
+        hi = bid >> lo_blocks_log;
+    }
+    auto gidx = [&](uint32_t j, uint32_t l) -> uint32_t {
+        return STRIDED ? ((hi << (s_hi + 1)) | (j << s_lo) | (lo_base + l)) : ((((bid << L_LOG) + l) << K) | j);
+    };
+    auto sidx = [&](uint32_t j, uint32_t l) -> uint32_t { return STRIDED ? ((j << L_LOG) + l) : ((l << K) + j); };
+    auto sget = [&](uint32_t e) -> Fr {
+        const uint4 a = plane0[e], b = plane1[e];
+        Fr r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+        return r;
+    };
+    auto sput = [&](uint32_t e, const Fr& x) {
+        plane0[e] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+        plane1[e] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+    };
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const uint32_t e = threadIdx.x + r * 512;
+        const uint32_t j = STRIDED ? (e >> L_LOG) : (e & (J - 1)), l = STRIDED ? (e & (L - 1)) : (e >> K);
+        const uint4* src = reinterpret_cast<const uint4*>(data + 32ull * gidx(j, l));
+        plane0[e] = src[0];
+        plane1[e] = src[1];
+    }
+    const uint32_t t = threadIdx.x;
+    const uint32_t l = STRIDED ? (t & (L - 1)) : (t >> (K - 1));
+    const uint32_t jj = STRIDED ? (t >> L_LOG) : (t & (J / 2 - 1));
+    auto stage_of = [&](int step) { return DIF ? (s_hi - step) : (s_lo + step); };
+    auto j0_of = [&](int st) -> uint32_t {
+        const uint32_t hb = st - s_lo;                     // log2 of the butterfly distance in j units
+        return ((jj >> hb) << (hb + 1)) | (jj & ((1u << hb) - 1));
+    };
+    auto tw_ptr = [&](int st, uint32_t j0) {
+        const uint32_t idx0 = gidx(j0, l);
+        return tw + 32ull * ((idx0 & ((1u << st) - 1)) << (log_n - 1 - st));
+    };
+    Fr w_next = Fr::load(tw_ptr(stage_of(0), j0_of(stage_of(0))));
+    __syncthreads();
+#pragma unroll
+    for (int step = 0; step < K; ++step) {
+        const int st = stage_of(step);
+        const uint32_t j0 = j0_of(st);
+        const uint32_t e0 = sidx(j0, l), e1 = sidx(j0 + (1u << (st - s_lo)), l);
+        const Fr w = w_next;
+        if (step + 1 < K) w_next = Fr::load(tw_ptr(stage_of(step + 1), j0_of(stage_of(step + 1))));
+        const Fr u = sget(e0), v = sget(e1);
+        if (DIF) {
+            sput(e0, u + v);
+            sput(e1, (u - v) * w);
+        } else {
+            const Fr x = v * w;
+            sput(e0, u + x);
+            sput(e1, u - x);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const uint32_t e = threadIdx.x + r * 512;
+        const uint32_t j = STRIDED ? (e >> L_LOG) : (e & (J - 1)), l2 = STRIDED ? (e & (L - 1)) : (e >> K);
+        const uint32_t g = gidx(j, l2);
+        if (scale) {
+            Fr x = sget(e) * Fr::load(scale + 32ull * g);
+            x.store(data + 32ull * g);
+        } else {
+            uint4* dst = reinterpret_cast<uint4*>(data + 32ull * g);
+            dst[0] = plane0[e];
+            dst[1] = plane1[e];
+        }
+    }
+}
+
+template <bool DIF>
+static bool launch_fast(uint8_t* data, const uint8_t* tw, const uint8_t* scale, int log_n, int s_lo, int s_hi, cudaStream_t st) {
+    if (log_n < 10) return false;
+    const int k = s_hi - s_lo + 1;
+    const uint32_t blocks = 1u << (log_n - 10);
+    const bool strided = s_lo > 0;
+    if (strided && s_lo < 10 - k) return false;
+#define ZKE_NTT_CASE(KK)                                                                                            \
+    case KK:                                                                                                       \
+        if (strided) ntt_pass_fast_kernel<DIF, KK, true><<<blocks, 512, 0, st>>>(data, tw, scale, log_n, s_lo);     \
+        else ntt_pass_fast_kernel<DIF, KK, false><<<blocks, 512, 0, st>>>(data, tw, scale, log_n, s_lo);            \
+        return true;
+    switch (k) {
+        ZKE_NTT_CASE(4) ZKE_NTT_CASE(5) ZKE_NTT_CASE(6) ZKE_NTT_CASE(7) ZKE_NTT_CASE(8)
+        default: return false;
+    }
+#undef ZKE_NTT_CASE
+}
+
 static void plan(int log_n, int* lo, int* hi, int* n_pass) {
     // split log_n stage bits into passes of at most 8 stages, as evenly as possible, top bits first
     int passes = (log_n + 7) / 8;
@@ -106,9 +213,11 @@ void launch_intt_dif(uint8_t* data, const NttTables& T, const uint8_t* scale_bit
     ZKE_COUNT_LAUNCH(np);
     const int tile_log = T.log_n < MAX_TILE_LOG ? T.log_n : MAX_TILE_LOG;
     const uint32_t blocks = 1u << (T.log_n - tile_log);
-    for (int p = 0; p < np; ++p)
-        ntt_pass_kernel<true><<<blocks, 1 << (tile_log - 1), 32u << tile_log, st>>>(
-            data, T.tw_inv, p == np - 1 ? scale_bitrev : nullptr, T.log_n, lo[p], hi[p], tile_log);
+    for (int p = 0; p < np; ++p) {
+        const uint8_t* sc = p == np - 1 ? scale_bitrev : nullptr;
+        if (launch_fast<true>(data, T.tw_inv, sc, T.log_n, lo[p], hi[p], st)) continue;
+        ntt_pass_kernel<true><<<blocks, 1 << (tile_log - 1), 32u << tile_log, st>>>(data, T.tw_inv, sc, T.log_n, lo[p], hi[p], tile_log);
+    }
 }
 
 void launch_ntt_dit(uint8_t* data, const NttTables& T, cudaStream_t st) {
@@ -117,9 +226,10 @@ void launch_ntt_dit(uint8_t* data, const NttTables& T, cudaStream_t st) {
     ZKE_COUNT_LAUNCH(np);
     const int tile_log = T.log_n < MAX_TILE_LOG ? T.log_n : MAX_TILE_LOG;
     const uint32_t blocks = 1u << (T.log_n - tile_log);
-    for (int p = np - 1; p >= 0; --p)
-        ntt_pass_kernel<false><<<blocks, 1 << (tile_log - 1), 32u << tile_log, st>>>(
-            data, T.tw_fwd, nullptr, T.log_n, lo[p], hi[p], tile_log);
+    for (int p = np - 1; p >= 0; --p) {
+        if (launch_fast<false>(data, T.tw_fwd, nullptr, T.log_n, lo[p], hi[p], st)) continue;
+        ntt_pass_kernel<false><<<blocks, 1 << (tile_log - 1), 32u << tile_log, st>>>(data, T.tw_fwd, nullptr, T.log_n, lo[p], hi[p], tile_log);
+    }
 }
 
 // c = a o b   (Montgomery in/out)
