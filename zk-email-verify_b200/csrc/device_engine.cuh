@@ -7,23 +7,34 @@
 namespace zke {
 namespace dev {
 
-static const int WITNESS_THREADS = 256;
+static const int WITNESS_THREADS = 512;
+static const uint32_t WITNESS_TERM_BUF = 8192;   // LC terms staged in shared memory per iteration (x 2 buffers x 8 B)
 
 // number of kernels launched by this library since load (reported by bench.py as gpu_launches)
 extern unsigned long long g_kernel_launches;
 #define ZKE_COUNT_LAUNCH(n) (::zke::dev::g_kernel_launches += (n))
 
-// Witness program resident in HBM (built once per circuit).
+// Witness program resident in HBM (built once per circuit): a STREAM of fixed-size op records, one per thread and
+// iteration.  The levelised program of the front-end is cut into iterations of WITNESS_THREADS ops (levels are padded
+// with no-ops), so the kernel needs no level table and no LC pool indirection: iteration k, thread t executes
+// ops[k * WITNESS_THREADS + t]; the LC terms of an iteration's ops are one contiguous block of `terms`, described by
+// iter_hdr[k], which the CTA stages into shared memory one iteration ahead (cp.async) while it evaluates the current
+// one.  Everything that does not depend on witness data is therefore prefetched; the only dependent memory round
+// trip left in an iteration is the gather of the witness values themselves.
+//   op record  : x = dst, y = code | nA << 8 | nB << 13 | nC << 18, z = operand (first term index / source variable /
+//                aux offset), w = shift | nbits << 16 (OP_SHRAND)
+//   term       : {variable, coefficient index}; blocks of an op are laid out [A | B | C]
+static const uint32_t WOP_NOP = 15;
 struct DevProgram {
-    const uint4* ops;            // {dst, a, b, c | code << 28}, sorted by level
-    const uint32_t* level_ptr;   // n_levels + 1
-    const uint32_t* lc_ptr;      // LC pool CSR
-    const uint2* lc_terms;       // {var, coef index}
+    const uint4* ops;            // [n_iters][WITNESS_THREADS]
+    const uint2* iter_hdr;       // [n_iters + 2]: {first term (even), term count (even)}
+    const uint2* terms;
     const uint32_t* aux;
     const uint8_t* coef_r;       // [n_coefs][32]: coefficient * R mod r  (Montgomery-scaled: (cR) (x) w = c*w)
     const uint8_t* small_inv;    // [n_small_inv][32]: x^-1 mod r in standard form, entry 0 unused
     uint32_t n_small_inv;
-    uint32_t n_levels, n_ops, n_vars, n_temps, n_outputs, n_inputs;
+    uint32_t n_iters, n_ops, n_vars, n_temps, n_outputs, n_inputs;
+    unsigned long long* trace;   // optional (diagnostics): clock64() of CTA 0 after every iteration
 };
 
 // R1CS matrices resident in HBM.

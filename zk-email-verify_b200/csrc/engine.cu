@@ -19,6 +19,7 @@ cudaError_t upload_constants_fixed_base(const FieldConsts*, const FieldConsts*);
 #include "engine.hpp"
 #include "ec_host.hpp"
 #include "setup_host.hpp"
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -110,7 +111,8 @@ struct zke_ctx {
     uint32_t max_batch = 0;
     cudaStream_t stream = nullptr;
     // circuit on device
-    DevBuf ops, level_ptr, lc_ptr, lc_terms, aux, coef_r, small_inv;
+    DevBuf ops, iter_hdr, lc_terms, aux, coef_r, small_inv;
+    std::vector<uint32_t> iter_info;   // per iteration {first op's record word 1, live ops, terms} (diagnostics)
     DevBuf a_ptr, a_terms, b_ptr, b_terms, c_ptr, c_terms;
     dev::DevProgram prog;
     dev::DevR1cs r1cs;
@@ -122,7 +124,11 @@ struct zke_ctx {
     DevBuf w_all, inputs, results, first_bad;
     // proving lanes: emails are dealt round-robin to `n_lanes` streams, each with its own NTT vectors and MSM
     // workspace, so that the latency-bound tails of one email's kernels overlap the saturating kernels of another
-    struct Lane { cudaStream_t st = nullptr; DevBuf va, vb, vc, vd, msm_ws; };
+    // Each lane owns two streams: `st` (high priority) carries the latency- / memory-bound kernels, `heavy` (low
+    // priority) the kernels that saturate the integer pipe (NTT passes, bucket accumulation of the H MSM).  When a
+    // block of a saturating kernel retires, the block scheduler serves pending high-priority blocks first, so the
+    // light kernels of one proof run inside the heavy kernels of another instead of queueing behind them.
+    struct Lane { cudaStream_t st = nullptr, heavy = nullptr; cudaEvent_t ev[6] = {}; DevBuf va, vb, vc, vd, msm_ws; };
     Lane lanes[ZKE_MAX_LANES];
     int n_lanes = 1, lanes_alloc = 0;
     uint8_t* results_host = nullptr;      // pinned, [max_batch][ZKE_RESULT_STRIDE]
@@ -130,6 +136,7 @@ struct zke_ctx {
     std::vector<cudaEvent_t> done;        // per email
     cudaEvent_t witness_done = nullptr;
     dev::MsmConfig cfg_w, cfg_h;
+    bool split_streams = true;   // ZKE_SPLIT_STREAMS=0: everything of a lane on one stream (experiments)
     uint32_t loaded = 0;         // number of witnesses currently resident
     uint32_t inputs_resident = 0; // batch size of the inputs currently in `inputs`
     std::vector<uint32_t> bad_host;
@@ -252,17 +259,107 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
 
     // witness program
     {
-        std::vector<uint32_t> packed(4 * c.ops.size());
-        for (size_t i = 0; i < c.ops.size(); ++i) {
-            const WOp& o = c.ops[i];
-            if (o.c >= (1u << 28)) throw std::runtime_error("witness program too large for the packed op format");
-            packed[4 * i + 0] = o.dst; packed[4 * i + 1] = o.a; packed[4 * i + 2] = o.b; packed[4 * i + 3] = o.c | (o.code << 28);
+        // Streamed witness program (device_engine.cuh): per level, ops sorted by kind / size so that the threads of an
+        // iteration do similar work, padded with no-ops to whole iterations of WITNESS_THREADS records; the LC terms
+        // of an iteration form one contiguous, 16-byte aligned block.
+        const uint32_t T = dev::WITNESS_THREADS;
+        std::vector<uint32_t> packed;                 // 4 words per record
+        std::vector<uint32_t> terms, hdr;             // 2 words per term / per iteration header
+        packed.reserve(4 * (c.ops.size() + (size_t)T * c.n_levels()));
+        terms.reserve(2 * c.lc_var.size() + 16);
+        auto lc_len = [&](uint32_t id) { return c.lc_ptr[id + 1] - c.lc_ptr[id]; };
+        // term word: coefficient index | k << 16 | kind << 24 (witness.cu: term_value)
+        if (c.coefs.size() > 0xffffu) throw std::runtime_error("too many distinct coefficients for the streamed witness program");
+        std::vector<uint32_t> coef_word(c.coefs.size());
+        for (size_t i = 0; i < c.coefs.size(); ++i) {
+            auto log2_exact = [](const U256& v) -> int {   // k if v == 2^k, else -1
+                int k = -1, bits = 0;
+                for (unsigned b = 0; b < 256; ++b) if (u256_bit(v, b)) { k = (int)b; ++bits; }
+                return bits == 1 ? k : -1;
+            };
+            U256 neg;
+            u256_sub(neg, fr_params().p, c.coefs[i]);
+            const int kp = log2_exact(c.coefs[i]), kn = log2_exact(neg);
+            uint32_t kind = 4, k = 0;
+            if (kp == 0) kind = 0;
+            else if (kn == 0) kind = 1;
+            else if (kp > 0 && kp <= 252) { kind = 2; k = (uint32_t)kp; }
+            else if (kn > 0 && kn <= 252) { kind = 3; k = (uint32_t)kn; }
+            coef_word[i] = (uint32_t)i | (k << 16) | (kind << 24);
         }
+        std::vector<uint32_t> order;
+        std::vector<uint64_t> keys;
+        for (uint32_t lvl = 0; lvl < c.n_levels(); ++lvl) {
+            const uint32_t beg = c.level_ptr[lvl], end = c.level_ptr[lvl + 1];
+            order.resize(end - beg);
+            for (uint32_t i = beg; i < end; ++i) order[i - beg] = i;
+            // Sort key: kind, then the positions of the terms that need a product (coefficient other than +-1) in the
+            // flattened [A | B | C] term list, then the term count.  Within an LC the product terms are emitted first
+            // (addition commutes), so the ops of a warp take the product branch of eval_lcs in the same term slots -
+            // or not at all: a warp only pays for a Montgomery product where some lane needs one.
+            auto key = [&](uint32_t i) -> uint64_t {
+                const WOp& o = c.ops[i];
+                if (o.code == OP_FPMUL) return ~0ull;
+                if (o.code == OP_INVZ) return 1ull << 62;
+                if (o.code == OP_SHRAND) return 0;
+                const uint32_t ids[3] = {o.a, o.b, o.c};
+                const uint32_t n_lc = o.code == OP_LIN ? 1 : 3;
+                uint64_t mask = 0;
+                uint32_t pos = 0;
+                for (uint32_t q = 0; q < n_lc; ++q) {
+                    uint32_t heavy = 0;
+                    for (uint32_t k = c.lc_ptr[ids[q]]; k < c.lc_ptr[ids[q] + 1]; ++k) heavy += (coef_word[c.lc_coef[k]] >> 24) >= 2;
+                    for (uint32_t t = 0; t < heavy && pos + t < 48; ++t) mask |= 1ull << (pos + t);
+                    pos += lc_len(ids[q]);
+                }
+                return ((uint64_t)(o.code == OP_QUAD ? 2 : 1) << 60) | (mask << 8) | std::min<uint32_t>(pos, 255);
+            };
+            keys.resize(end - beg);
+            for (uint32_t i = beg; i < end; ++i) keys[i - beg] = key(i);
+            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keys[x - beg] > keys[y - beg]; });
+            for (size_t base = 0; base < order.size(); base += T) {
+                const uint32_t first_term = (uint32_t)(terms.size() / 2);
+                for (uint32_t t = 0; t < T; ++t) {
+                    uint32_t rec[4] = {0, dev::WOP_NOP, 0, 0};
+                    if (base + t < order.size()) {
+                        const WOp& o = c.ops[order[base + t]];
+                        rec[0] = o.dst;
+                        if (o.code == OP_LIN || o.code == OP_QUAD) {
+                            const uint32_t ids[3] = {o.a, o.b, o.c};
+                            const uint32_t n_lc = o.code == OP_LIN ? 1 : 3;
+                            uint32_t n[3] = {0, 0, 0};
+                            rec[2] = (uint32_t)(terms.size() / 2);
+                            for (uint32_t q = 0; q < n_lc; ++q) {
+                                n[q] = lc_len(ids[q]);
+                                if (n[q] > 31) throw std::runtime_error("linear combination too long for the streamed witness program");
+                                for (int pass = 0; pass < 2; ++pass)   // product terms first
+                                    for (uint32_t k = c.lc_ptr[ids[q]]; k < c.lc_ptr[ids[q] + 1]; ++k)
+                                        if (((coef_word[c.lc_coef[k]] >> 24) >= 2) == (pass == 0)) { terms.push_back(c.lc_var[k]); terms.push_back(coef_word[c.lc_coef[k]]); }
+                            }
+                            rec[1] = o.code | (n[0] << 8) | (n[1] << 13) | (n[2] << 18);
+                        } else if (o.code == OP_SHRAND) {
+                            if (o.b > 0xffffu || o.c > 0xffffu) throw std::runtime_error("OP_SHRAND operand out of range");
+                            rec[1] = o.code; rec[2] = o.a; rec[3] = o.b | (o.c << 16);
+                        } else {
+                            rec[1] = o.code; rec[2] = o.a;
+                        }
+                    }
+                    packed.insert(packed.end(), rec, rec + 4);
+                }
+                if ((terms.size() / 2) & 1) { terms.push_back(0); terms.push_back(0); }   // keep blocks 16-byte aligned
+                hdr.push_back(first_term);
+                hdr.push_back((uint32_t)(terms.size() / 2) - first_term);
+                x->iter_info.push_back(packed[packed.size() - 4 * T + 1]);
+                x->iter_info.push_back((uint32_t)std::min<size_t>(T, order.size() - base));
+                x->iter_info.push_back((uint32_t)(terms.size() / 2) - first_term);
+            }
+        }
+        const uint32_t n_iters = (uint32_t)(hdr.size() / 2);
+        for (int q = 0; q < 4; ++q) hdr.push_back(q & 1 ? 0 : (uint32_t)(terms.size() / 2));   // two sentinel headers
+        if (packed.empty()) packed.resize(4 * T, 0);
+        for (int q = 0; q < 8; ++q) terms.push_back(0);
         x->ops.upload(packed);
-        x->level_ptr.upload(c.level_ptr);
-        x->lc_ptr.upload(c.lc_ptr);
-        std::vector<uint32_t> terms(2 * c.lc_var.size());
-        for (size_t i = 0; i < c.lc_var.size(); ++i) { terms[2 * i] = c.lc_var[i]; terms[2 * i + 1] = c.lc_coef[i]; }
+        x->iter_hdr.upload(hdr);
         x->lc_terms.upload(terms);
         std::vector<uint32_t> aux = c.aux;
         if (aux.empty()) aux.push_back(0);
@@ -279,10 +376,11 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         for (uint32_t i = 0; i < NSMALL; ++i) inv_std[i] = inv[i].to_u256();
         x->small_inv.upload(inv_std);
         dev::DevProgram& P = x->prog;
-        P.ops = (const uint4*)x->ops.p; P.level_ptr = (const uint32_t*)x->level_ptr.p; P.lc_ptr = (const uint32_t*)x->lc_ptr.p;
-        P.lc_terms = (const uint2*)x->lc_terms.p; P.aux = (const uint32_t*)x->aux.p; P.coef_r = x->coef_r.p;
+        P.ops = (const uint4*)x->ops.p; P.iter_hdr = (const uint2*)x->iter_hdr.p;
+        P.terms = (const uint2*)x->lc_terms.p; P.aux = (const uint32_t*)x->aux.p; P.coef_r = x->coef_r.p;
         P.small_inv = x->small_inv.p; P.n_small_inv = NSMALL;
-        P.n_levels = c.n_levels(); P.n_ops = (uint32_t)c.ops.size(); P.n_vars = c.n_vars; P.n_temps = c.n_temps;
+        P.trace = nullptr;
+        P.n_iters = n_iters; P.n_ops = (uint32_t)c.ops.size(); P.n_vars = c.n_vars; P.n_temps = c.n_temps;
         P.n_outputs = c.n_outputs; P.n_inputs = c.n_inputs();
     }
     // R1CS
@@ -347,10 +445,15 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         ws = std::max(ws, dev::MsmPlan<dev::Fq2>::workspace_bytes(c.n_vars, x->cfg_w));
         int want = 8;
         if (const char* e = getenv("ZKE_LANES")) want = atoi(e);
+        if (const char* e = getenv("ZKE_SPLIT_STREAMS")) x->split_streams = atoi(e) != 0;
         want = std::max(1, std::min(ZKE_MAX_LANES, std::min<int>(want, (int)max_batch)));
         for (int i = 0; i < want; ++i) {
             zke_ctx::Lane& L = x->lanes[i];
-            CUDA_OK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+            int prio_least = 0, prio_greatest = 0;
+            CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+            CUDA_OK(cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, prio_greatest));
+            CUDA_OK(cudaStreamCreateWithPriority(&L.heavy, cudaStreamNonBlocking, prio_least));
+            for (auto& e : L.ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             L.va.alloc(N * 32); L.vb.alloc(N * 32); L.vc.alloc(N * 32); L.vd.alloc(N * 32);
             L.msm_ws.alloc(ws);
         }
@@ -385,6 +488,21 @@ static void do_witness(zke_ctx* x, const uint8_t* inputs, size_t batch) {
     }
     size_t p0 = 0;
     if (x->profile) p0 = x->mark();
+    if (const char* tp = getenv("ZKE_WITNESS_TRACE")) {   // diagnostics: per-iteration clock of CTA 0 -> file
+        DevBuf tr;
+        tr.alloc(8 * ((size_t)x->prog.n_iters + 1));
+        dev::DevProgram P = x->prog;
+        P.trace = (unsigned long long*)tr.p;
+        dev::launch_witness(P, x->w_all.p, x->stride, x->inputs.p, (uint32_t)batch, x->stream);
+        CUDA_OK(cudaStreamSynchronize(x->stream));
+        std::vector<unsigned long long> h(x->prog.n_iters);
+        CUDA_OK(cudaMemcpy(h.data(), tr.p, 8 * h.size(), cudaMemcpyDeviceToHost));
+        if (FILE* f = fopen(tp, "wb")) {
+            fwrite(h.data(), 8, h.size(), f);
+            fwrite(x->iter_info.data(), 4, x->iter_info.size(), f);
+            fclose(f);
+        }
+    }
     dev::launch_witness(x->prog, x->w_all.p, x->stride, x->inputs.p, (uint32_t)batch, x->stream);
     if (x->profile) x->spans.push_back({ZKE_STAGE_WITNESS, p0, x->mark()});
     x->loaded = (uint32_t)batch;
@@ -439,6 +557,7 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
     const uint32_t N = 1u << zk->log_n, m = c.n_vars, l = c.n_public();
     const bool prof = x->profile;
     const int n_lanes = prof ? 1 : x->n_lanes;     // stage timing is only meaningful without overlap
+    if (const char* e = getenv("ZKE_SPLIT_STREAMS")) x->split_streams = atoi(e) != 0;
     // the witnesses were produced on the main stream; the lanes start after it (and after the public signals copy)
     if (l) CUDA_OK(cudaMemcpy2DAsync(x->publics_host, (size_t)l * 32, x->w_all.p + 32, x->stride * 32, (size_t)l * 32, batch, cudaMemcpyDeviceToHost, x->stream));
     CUDA_OK(cudaEventRecord(x->witness_done, x->stream));
@@ -452,37 +571,50 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
         size_t t0 = 0, t1 = 0;
         CUDA_OK(cudaMemsetAsync(flag, 0xff, 4, st));
         if (prof) t0 = x->mark(st);
+        // `hv` = the lane's low-priority stream for the saturating kernels (profiling: everything on `st`)
+        cudaStream_t hv = (prof || !x->split_streams) ? st : L.heavy;
         dev::launch_build_ab(x->r1cs, w, L.va.p, L.vb.p, N, flag, st);
         if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MATVEC, t0, t1}); t0 = t1; }
         dev::launch_hadamard(L.va.p, L.vb.p, L.vc.p, N, st);
-        dev::launch_intt_dif(L.va.p, x->ntt, x->coset_scale.p, st);
-        dev::launch_intt_dif(L.vb.p, x->ntt, x->coset_scale.p, st);
-        dev::launch_intt_dif(L.vc.p, x->ntt, x->coset_scale.p, st);
-        dev::launch_ntt_dit(L.va.p, x->ntt, st);
-        dev::launch_ntt_dit(L.vb.p, x->ntt, st);
-        dev::launch_ntt_dit(L.vc.p, x->ntt, st);
-        dev::launch_quotient(L.va.p, L.vb.p, L.vc.p, L.vd.p, N, st);
+        if (hv != st) { CUDA_OK(cudaEventRecord(L.ev[0], st)); CUDA_OK(cudaStreamWaitEvent(hv, L.ev[0], 0)); }
+        dev::launch_intt_dif(L.va.p, x->ntt, x->coset_scale.p, hv);
+        dev::launch_intt_dif(L.vb.p, x->ntt, x->coset_scale.p, hv);
+        dev::launch_intt_dif(L.vc.p, x->ntt, x->coset_scale.p, hv);
+        dev::launch_ntt_dit(L.va.p, x->ntt, hv);
+        dev::launch_ntt_dit(L.vb.p, x->ntt, hv);
+        dev::launch_ntt_dit(L.vc.p, x->ntt, hv);
+        dev::launch_quotient(L.va.p, L.vb.p, L.vc.p, L.vd.p, N, hv);
+        if (hv != st) CUDA_OK(cudaEventRecord(L.ev[1], hv));
         if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_NTT, t0, t1}); t0 = t1; }
-        dev::MsmPlan<dev::Fq>::run(zk->A.p, w, m, x->cfg_w, L.msm_ws.p, res + 0 * ZKE_RES_G1_BLOCK, st);
+        // the witness MSMs do not depend on the transforms: with split streams they run on `st` while the lane's NTT
+        // passes are still in flight on `hv` (the MSM workspace is only touched from `st`-ordered work)
+        uint8_t* ws_w = L.msm_ws.p;
+        dev::MsmPlan<dev::Fq>::run(zk->A.p, w, m, x->cfg_w, ws_w, res + 0 * ZKE_RES_G1_BLOCK, st);
         if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MSM_A, t0, t1}); t0 = t1; }
-        dev::MsmPlan<dev::Fq>::run(zk->B1.p, w, m, x->cfg_w, L.msm_ws.p, res + 1 * ZKE_RES_G1_BLOCK, st);
+        dev::MsmPlan<dev::Fq>::run(zk->B1.p, w, m, x->cfg_w, ws_w, res + 1 * ZKE_RES_G1_BLOCK, st);
         if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MSM_B1, t0, t1}); t0 = t1; }
-        dev::MsmPlan<dev::Fq>::run(zk->C.p, w, m, x->cfg_w, L.msm_ws.p, res + 2 * ZKE_RES_G1_BLOCK, st);
+        dev::MsmPlan<dev::Fq>::run(zk->C.p, w, m, x->cfg_w, ws_w, res + 2 * ZKE_RES_G1_BLOCK, st);
         if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MSM_C, t0, t1}); t0 = t1; }
-        if (prof) {
-            size_t i0, i1;
-            cudaEvent_t evs[2];
-            evs[0] = x->ev(&i0); evs[1] = x->ev(&i1);
-            dev::MsmPlan<dev::Fq>::run(zk->H.p, L.vd.p, N, x->cfg_h, L.msm_ws.p, res + 3 * ZKE_RES_G1_BLOCK, st, evs);
-            x->spans.push_back({ZKE_STAGE_MSM_H_BUCKETS, i0, i1});
-            t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MSM_H, t0, t1}); t0 = t1;
-        } else {
-            dev::MsmPlan<dev::Fq>::run(zk->H.p, L.vd.p, N, x->cfg_h, L.msm_ws.p, res + 3 * ZKE_RES_G1_BLOCK, st);
-        }
-        dev::MsmPlan<dev::Fq2>::run(zk->B2.p, w, m, x->cfg_w, L.msm_ws.p, res + 4 * ZKE_RES_G1_BLOCK, st);
+        dev::MsmPlan<dev::Fq2>::run(zk->B2.p, w, m, x->cfg_w, ws_w, res + 4 * ZKE_RES_G1_BLOCK, st);
         if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MSM_B2, t0, t1}); t0 = t1; }
+        if (hv != st) CUDA_OK(cudaStreamWaitEvent(st, L.ev[1], 0));
+        {
+            dev::MsmPlan<dev::Fq>::Heavy heavy{hv, L.ev[2], L.ev[3]};
+            if (prof) {
+                size_t i0, i1;
+                cudaEvent_t evs[2];
+                evs[0] = x->ev(&i0); evs[1] = x->ev(&i1);
+                dev::MsmPlan<dev::Fq>::run(zk->H.p, L.vd.p, N, x->cfg_h, L.msm_ws.p, res + 3 * ZKE_RES_G1_BLOCK, st, evs, &heavy);
+                x->spans.push_back({ZKE_STAGE_MSM_H_BUCKETS, i0, i1});
+                t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MSM_H, t0, t1}); t0 = t1;
+            } else {
+                dev::MsmPlan<dev::Fq>::run(zk->H.p, L.vd.p, N, x->cfg_h, L.msm_ws.p, res + 3 * ZKE_RES_G1_BLOCK, st, nullptr, &heavy);
+            }
+        }
         CUDA_OK(cudaMemcpyAsync(x->results_host + (size_t)ZKE_RESULT_STRIDE * e, res, ZKE_RESULT_STRIDE, cudaMemcpyDeviceToHost, st));
         CUDA_OK(cudaEventRecord(x->done[e], st));
+        // the lane's next email reuses va..vd on `hv`; its first kernels run on `st` (after this point) and `hv`
+        // only starts after an event recorded on `st`, so the order is already enforced
     }
 
     // host tail, overlapped with the GPU work of the later emails
@@ -525,7 +657,7 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
         write_fq(out + 192, C.x); write_fq(out + 224, C.y);
     }
     CUDA_OK(cudaStreamSynchronize(x->stream));
-    for (int i = 0; i < n_lanes; ++i) CUDA_OK(cudaStreamSynchronize(x->lanes[i].st));
+    for (int i = 0; i < n_lanes; ++i) { CUDA_OK(cudaStreamSynchronize(x->lanes[i].st)); CUDA_OK(cudaStreamSynchronize(x->lanes[i].heavy)); }
     // later work on the main stream (next witness batch) must not overtake the lanes: they are idle now
     if (prof) x->collect();
     if (publics_out && l) memcpy(publics_out, x->publics_host, (size_t)l * 32 * batch);
@@ -616,7 +748,11 @@ void zke_ctx_close(zke_ctx* x) {
     for (auto e : x->ev_pool) cudaEventDestroy(e);
     for (auto e : x->done) cudaEventDestroy(e);
     if (x->witness_done) cudaEventDestroy(x->witness_done);
-    for (int i = 0; i < x->lanes_alloc; ++i) if (x->lanes[i].st) cudaStreamDestroy(x->lanes[i].st);
+    for (int i = 0; i < x->lanes_alloc; ++i) {
+        if (x->lanes[i].st) cudaStreamDestroy(x->lanes[i].st);
+        if (x->lanes[i].heavy) cudaStreamDestroy(x->lanes[i].heavy);
+        for (auto e : x->lanes[i].ev) if (e) cudaEventDestroy(e);
+    }
     if (x->results_host) cudaFreeHost(x->results_host);
     if (x->publics_host) cudaFreeHost(x->publics_host);
     if (x->stream) cudaStreamDestroy(x->stream);

@@ -18,4 +18,4 @@ struct zke_circuit {
 #define ZKE_RES_G2_BLOCK (64 * 256)
 #define ZKE_RES_FLAG_OFF (4 * ZKE_RES_G1_BLOCK + ZKE_RES_G2_BLOCK)
 #define ZKE_RESULT_STRIDE (ZKE_RES_FLAG_OFF + 256)
-#define ZKE_MAX_LANES 8
+#define ZKE_MAX_LANES 16

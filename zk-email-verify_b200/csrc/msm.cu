@@ -14,6 +14,7 @@
 // (~300 IMAD each) per 64-byte point (SURVEY 8(d) "Which roofline bounds what").
 #include "device_engine.cuh"
 #include "msm.cuh"
+#include <algorithm>
 #include <cstdlib>
 
 namespace zke {
@@ -387,7 +388,7 @@ size_t MsmPlan<F>::workspace_bytes(uint32_t n, const MsmConfig& cfg) {
 
 template <class F>
 void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, const MsmConfig& cfg, uint8_t* ws,
-                     uint8_t* result, cudaStream_t st, cudaEvent_t* ev) {
+                     uint8_t* result, cudaStream_t st, cudaEvent_t* ev, const Heavy* heavy) {
     Digits D;
     D.c = cfg.c;
     D.n_windows = (255 + cfg.c - 1) / cfg.c;
@@ -463,17 +464,29 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     digit_scatter_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, offsets, cursor, entries);
     exclusive_scan(hist, n_buckets, D.chunk, 0, chunk_off, tiles, st);
     fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, chunk_off, n_buckets, D.chunk, 0, work_bucket);
+    cudaStream_t st_light = st;
+    if (heavy && heavy->st != st) {
+        cudaEventRecord(heavy->before, st);
+        cudaStreamWaitEvent(heavy->st, heavy->before, 0);
+        st = heavy->st;
+    }
     if (ev) cudaEventRecord(ev[0], st);
     {
         // blocks per SM the bucket kernel is compiled for (register cap 128 / 96 / 80): more resident warps hide the
         // IMAD.WIDE carry-chain latency; tunable for experiments with ZKE_CHUNK_MINB
-        static int minb = -1;
-        if (minb < 0) { const char* e = getenv("ZKE_CHUNK_MINB"); minb = e ? atoi(e) : (sizeof(F) == 32 ? 5 : 4); }
-        if (minb >= 6) chunk_sum_kernel<F, 6><<<148 * 6 * 4, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
-        else if (minb == 5) chunk_sum_kernel<F, 5><<<148 * 5 * 4, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
-        else chunk_sum_kernel<F, 4><<<148 * 4 * 4, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
+        int minb = sizeof(F) == 32 ? 5 : 4, waves = 4;
+        if (const char* e = getenv("ZKE_CHUNK_MINB")) minb = atoi(e);
+        if (const char* e = getenv("ZKE_CHUNK_WAVES")) waves = std::max(1, atoi(e));
+        if (minb >= 6) chunk_sum_kernel<F, 6><<<148 * 6 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
+        else if (minb == 5) chunk_sum_kernel<F, 5><<<148 * 5 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
+        else chunk_sum_kernel<F, 4><<<148 * 4 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
     }
     if (ev) cudaEventRecord(ev[1], st);
+    if (st != st_light) {
+        cudaEventRecord(heavy->after, st);
+        cudaStreamWaitEvent(st_light, heavy->after, 0);
+        st = st_light;
+    }
     // extra passes over the per-chunk partial sums
     uint8_t *items = partial, *items_next = partial2;
     uint32_t *off_cur = chunk_off, *off_next = off2;

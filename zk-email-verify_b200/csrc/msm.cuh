@@ -37,8 +37,13 @@ template <class F>
 struct MsmPlan {
     static size_t workspace_bytes(uint32_t n, const MsmConfig& cfg);
     // ev (optional): two events recorded immediately before / after the bucket-accumulation kernel (profiling)
+    // heavy (optional): the bucket-accumulation kernel - the one kernel of an MSM that saturates the integer pipe - is
+    // launched on heavy->st instead of `st` (the two streams are ordered by heavy->before / heavy->after), so that a
+    // caller can keep the saturating kernels of all proofs on low-priority streams and let the latency-bound rest of
+    // other proofs slip in between their blocks.
+    struct Heavy { cudaStream_t st; cudaEvent_t before, after; };
     static void run(const uint8_t* points, const uint8_t* scalars, uint32_t n, const MsmConfig& cfg, uint8_t* workspace,
-                    uint8_t* result, cudaStream_t st, cudaEvent_t* ev = nullptr);
+                    uint8_t* result, cudaStream_t st, cudaEvent_t* ev = nullptr, const Heavy* heavy = nullptr);
 };
 
 }  // namespace dev

@@ -94,13 +94,14 @@ ntt_pass_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, cons
 template <bool DIF, int K, bool STRIDED>
 __global__ void __launch_bounds__(512)
 ntt_pass_fast_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, const uint8_t* __restrict__ scale,
-                     int log_n, int s_lo) {
+                     int log_n, int s_lo_arg) {
+    const int s_lo = STRIDED ? s_lo_arg : 0;   // the contiguous pass always starts at stage 0 (compile-time stages)
     constexpr int TILE_LOG = 10, TILE = 1 << TILE_LOG, J = 1 << K, L_LOG = TILE_LOG - K, L = 1 << L_LOG;
     __shared__ uint4 plane0[TILE], plane1[TILE];
     const int s_hi = s_lo + K - 1;
     const uint32_t bid = blockIdx.x;
     uint32_t hi = 0, lo_base = 0;
-    if (STRIDED) {
+    if constexpr (STRIDED) {
         const uint32_t lo_blocks_log = s_lo - L_LOG;
         lo_base = (bid & ((1u << lo_blocks_log) - 1)) << L_LOG;
         hi = bid >> lo_blocks_log;
@@ -148,11 +149,12 @@ ntt_pass_fast_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw,
         const Fr w = w_next;
         if (step + 1 < K) w_next = Fr::load(tw_ptr(stage_of(step + 1), j0_of(stage_of(step + 1))));
         const Fr u = sget(e0), v = sget(e1);
+        const bool trivial = !STRIDED && st == 0;   // stage 0: every twiddle is omega^0 = 1, no product
         if (DIF) {
             sput(e0, u + v);
-            sput(e1, (u - v) * w);
+            sput(e1, trivial ? (u - v) : (u - v) * w);
         } else {
-            const Fr x = v * w;
+            const Fr x = trivial ? v : v * w;
             sput(e0, u + x);
             sput(e1, u - x);
         }
