@@ -40,7 +40,7 @@ struct DevProgram {
 // R1CS matrices resident in HBM.
 struct DevR1cs {
     const uint32_t *a_ptr, *b_ptr, *c_ptr;
-    const uint2 *a_terms, *b_terms, *c_terms;   // {var, coef index}
+    const uint2 *a_terms, *b_terms, *c_terms;   // {var, coefficient word (lc_term.cuh)}
     const uint8_t* coef_r;                      // same table as DevProgram::coef_r
     uint32_t n_constraints, n_public, n_vars;
 };
@@ -52,7 +52,9 @@ void launch_witness(const DevProgram& P, uint8_t* w_all, size_t stride_elems, co
 // a[i] = <A_i, w>, b[i] = <B_i, w> in Montgomery form for i < n_constraints, the n_public + 1 extra rows of the
 // Groth16 QAP (a = w_j, b = 0), zero padding up to n; also checks <A,w><B,w> = <C,w> and atomically records the
 // smallest violated row in *first_bad (initialised to 0xffffffff by the caller).
-void launch_build_ab(const DevR1cs& R, const uint8_t* w, uint8_t* a_out, uint8_t* b_out, uint32_t n, uint32_t* first_bad, cudaStream_t st);
+// c_out (optional): a_i * b_i in Montgomery form (fused Hadamard product).  R1CS term words use the encoding of
+// lc_term.cuh.
+void launch_build_ab(const DevR1cs& R, const uint8_t* w, uint8_t* a_out, uint8_t* b_out, uint8_t* c_out, uint32_t n, uint32_t* first_bad, cudaStream_t st);
 
 }  // namespace dev
 }  // namespace zke

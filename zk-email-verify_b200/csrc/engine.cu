@@ -112,6 +112,7 @@ struct zke_ctx {
     cudaStream_t stream = nullptr;
     // circuit on device
     DevBuf ops, iter_hdr, lc_terms, aux, coef_r, small_inv;
+    std::vector<uint32_t> coef_word;   // per interned coefficient: index | k << 16 | kind << 24 (lc_term.cuh)
     std::vector<uint32_t> iter_info;   // per iteration {first op's record word 1, live ops, terms} (diagnostics)
     DevBuf a_ptr, a_terms, b_ptr, b_terms, c_ptr, c_terms;
     dev::DevProgram prog;
@@ -270,7 +271,8 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         auto lc_len = [&](uint32_t id) { return c.lc_ptr[id + 1] - c.lc_ptr[id]; };
         // term word: coefficient index | k << 16 | kind << 24 (witness.cu: term_value)
         if (c.coefs.size() > 0xffffu) throw std::runtime_error("too many distinct coefficients for the streamed witness program");
-        std::vector<uint32_t> coef_word(c.coefs.size());
+        std::vector<uint32_t>& coef_word = x->coef_word;
+        coef_word.assign(c.coefs.size(), 0);
         for (size_t i = 0; i < c.coefs.size(); ++i) {
             auto log2_exact = [](const U256& v) -> int {   // k if v == 2^k, else -1
                 int k = -1, bits = 0;
@@ -385,9 +387,9 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
     }
     // R1CS
     {
-        auto up_terms = [](const std::vector<uint32_t>& var, const std::vector<uint32_t>& coef, DevBuf& dst) {
+        auto up_terms = [&](const std::vector<uint32_t>& var, const std::vector<uint32_t>& coef, DevBuf& dst) {
             std::vector<uint32_t> t(2 * var.size() + 2);
-            for (size_t i = 0; i < var.size(); ++i) { t[2 * i] = var[i]; t[2 * i + 1] = coef[i]; }
+            for (size_t i = 0; i < var.size(); ++i) { t[2 * i] = var[i]; t[2 * i + 1] = x->coef_word[coef[i]]; }
             dst.upload(t);
         };
         x->a_ptr.upload(c.a_ptr); x->b_ptr.upload(c.b_ptr); x->c_ptr.upload(c.c_ptr);
@@ -518,7 +520,7 @@ static int do_check(zke_ctx* x, size_t batch, int32_t* status, std::string& msg)
     else { ta.alloc((size_t)rows * 32); tb.alloc((size_t)rows * 32); pa = ta.p; pb = tb.p; }
     CUDA_OK(cudaMemsetAsync(x->first_bad.p, 0xff, 4 * batch, x->stream));
     for (size_t e = 0; e < batch; ++e) {
-        dev::launch_build_ab(x->r1cs, x->w_all.p + 32 * x->stride * e, pa, pb, rows, (uint32_t*)x->first_bad.p + e, x->stream);
+        dev::launch_build_ab(x->r1cs, x->w_all.p + 32 * x->stride * e, pa, pb, nullptr, rows, (uint32_t*)x->first_bad.p + e, x->stream);
     }
     CUDA_OK(cudaMemcpyAsync(x->bad_host.data(), x->first_bad.p, 4 * batch, cudaMemcpyDeviceToHost, x->stream));
     CUDA_OK(cudaStreamSynchronize(x->stream));
@@ -573,9 +575,8 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
         if (prof) t0 = x->mark(st);
         // `hv` = the lane's low-priority stream for the saturating kernels (profiling: everything on `st`)
         cudaStream_t hv = (prof || !x->split_streams) ? st : L.heavy;
-        dev::launch_build_ab(x->r1cs, w, L.va.p, L.vb.p, N, flag, st);
+        dev::launch_build_ab(x->r1cs, w, L.va.p, L.vb.p, L.vc.p, N, flag, st);
         if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MATVEC, t0, t1}); t0 = t1; }
-        dev::launch_hadamard(L.va.p, L.vb.p, L.vc.p, N, st);
         if (hv != st) { CUDA_OK(cudaEventRecord(L.ev[0], st)); CUDA_OK(cudaStreamWaitEvent(hv, L.ev[0], 0)); }
         dev::launch_intt_dif(L.va.p, x->ntt, x->coset_scale.p, hv);
         dev::launch_intt_dif(L.vb.p, x->ntt, x->coset_scale.p, hv);

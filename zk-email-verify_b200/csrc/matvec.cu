@@ -3,6 +3,7 @@
 // <A_i,w><B_i,w> = <C_i,w>, and writes a_i, b_i in Montgomery form for the NTTs.
 // HBM-bound gather: nnz * 8 B of (var, coef) pairs + one 32-byte witness read per non-zero, 2 * 32 * N written.
 #include "device_engine.cuh"
+#include "lc_term.cuh"
 
 namespace zke {
 namespace dev {
@@ -12,38 +13,39 @@ __device__ __forceinline__ Fr row_dot(const uint32_t* ptr, const uint2* terms, c
     const uint32_t beg = ptr[row], end = ptr[row + 1];
     for (uint32_t k = beg; k < end; ++k) {
         const uint2 t = terms[k];
-        Fr x = Fr::load(w + 32ull * t.x);
-        if (t.y == 0) acc = acc + x;
-        else if (t.y == 1) acc = acc - x;
-        else acc = acc + Fr::load(coef_r + 32ull * t.y) * x;
+        const TermVal tv = term_value(coef_r, t, Fr::load(w + 32ull * t.x));   // +-1 / +-2^k coefficients: no product
+        acc = tv.neg ? acc - tv.v : acc + tv.v;
     }
     return acc;
 }
 
+// c_out (optional): c_i = a_i b_i in Montgomery form (the third vector of the quotient computation; snarkjs derives it
+// from a and b rather than from the C matrix) - fused here so that no separate Hadamard pass is needed.
 __global__ void __launch_bounds__(256)
 build_ab_kernel(DevR1cs R, const uint8_t* __restrict__ w, uint8_t* __restrict__ a_out, uint8_t* __restrict__ b_out,
-                uint32_t n, uint32_t* first_bad) {
+                uint8_t* __restrict__ c_out, uint32_t n, uint32_t* first_bad) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Fr a = Fr::zero(), b = Fr::zero();
+    Fr a = Fr::zero(), b = Fr::zero(), c = Fr::zero();
     if (i < R.n_constraints) {
         a = row_dot(R.a_ptr, R.a_terms, R.coef_r, w, i);
         b = row_dot(R.b_ptr, R.b_terms, R.coef_r, w, i);
-        Fr c = row_dot(R.c_ptr, R.c_terms, R.coef_r, w, i);
-        Fr ab = (a * b) * Fr::r2();   // standard form product
-        if (ab != c) atomicMin(first_bad, i);
+        const Fr c_lc = row_dot(R.c_ptr, R.c_terms, R.coef_r, w, i);
         a = a.to_mont();
+        if ((a * b) != c_lc) atomicMin(first_bad, i);   // (aR) (x) b = a b in standard form
         b = b.to_mont();
+        if (c_out) c = a * b;
     } else if (i <= R.n_constraints + R.n_public) {
         // extra rows that make the public-input polynomials independent: a = w_j, b = 0
         a = Fr::load(w + 32ull * (i - R.n_constraints)).to_mont();
     }
     a.store(a_out + 32ull * i);
     b.store(b_out + 32ull * i);
+    if (c_out) c.store(c_out + 32ull * i);
 }
 
-void launch_build_ab(const DevR1cs& R, const uint8_t* w, uint8_t* a_out, uint8_t* b_out, uint32_t n, uint32_t* first_bad, cudaStream_t st) {
-    build_ab_kernel<<<(n + 255) / 256, 256, 0, st>>>(R, w, a_out, b_out, n, first_bad);
+void launch_build_ab(const DevR1cs& R, const uint8_t* w, uint8_t* a_out, uint8_t* b_out, uint8_t* c_out, uint32_t n, uint32_t* first_bad, cudaStream_t st) {
+    build_ab_kernel<<<(n + 255) / 256, 256, 0, st>>>(R, w, a_out, b_out, c_out, n, first_bad);
     ZKE_COUNT_LAUNCH(1);
 }
 
