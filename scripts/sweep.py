@@ -3,7 +3,7 @@
 import ctypes, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "zk-email-verify_b200", "host")); sys.path.insert(0, os.path.join(ROOT, "tests"))
-os.environ.setdefault("ZKE_LANES", "16")
+os.environ.setdefault("ZKE_LANES", "8")
 import torch
 import zkemail_b200 as z
 import bench

@@ -14,6 +14,8 @@ struct MsmConfig {
     // because the proving key is reused for every proof): all windows then share ONE bucket set, so the window
     // count no longer multiplies the bucket count, c can grow (fewer additions per point) and no Horner tail is left
     bool precomputed = false;
+    // > 0: the first ba_levels levels of every chunk's addition tree use batched-affine additions (ba.cuh)
+    int ba_levels = 0;
 };
 MsmConfig msm_config_witness();          // witness-scalar MSMs (mostly 0 / 1 / byte-sized scalars)
 MsmConfig msm_config_full(uint32_t n, bool precomputed);   // full-width scalars (the H MSM)
