@@ -56,7 +56,7 @@ uint32_t Circuit::domain_log2() const {
 }
 
 // ---------------------------------------------------------------- Builder
-static const size_t LC_FANIN = 16;  // longer program LCs are split into a tree of scratch partial sums
+static const size_t LC_FANIN = 8;   // longer program LCs are split into a tree of scratch partial sums
 
 Builder::Builder(const std::string& name) {
     c_.name = name;
