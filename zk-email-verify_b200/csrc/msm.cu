@@ -475,7 +475,7 @@ template <class F>
 static void launch_ba(int levels, int waves, const uint8_t* points, const uint32_t* entries, const uint32_t* offsets, const uint32_t* hist,
                       const uint32_t* chunk_off, const uint32_t* work_bucket, uint32_t n_buckets, uint32_t chunk, uint8_t* partial,
                       uint8_t* scratch, size_t cap, cudaStream_t st) {
-    constexpr int MINB = 4;
+    constexpr int MINB = 3;   // 168 registers: no spills in the pair loops (at 128 the compiler spills ~1 KB into them)
     (void)waves;
     const int grid = 148 * MINB;     // every thread walks all of its chunks between two block-wide inversions
     BaScratch<F> S;
@@ -497,7 +497,13 @@ static size_t ba_scratch_bytes(size_t chunk, size_t cap) {
 
 // ---------------------------------------------------------------- host orchestration
 #if defined(ZKE_MSM_G1)
-MsmConfig msm_config_witness() { MsmConfig c; c.c = 8; c.chunk = 32; c.group = 8; c.classify = true; c.extra_passes = 2; return c; }
+MsmConfig msm_config_witness() {
+    MsmConfig c; c.c = 8; c.chunk = 32; c.group = 8; c.classify = true; c.extra_passes = 2;
+    if (const char* e = getenv("ZKE_W_C")) c.c = std::max(4, std::min(16, atoi(e)));          // experiments
+    if (const char* e = getenv("ZKE_W_CHUNK")) c.chunk = (uint32_t)std::max(8, atoi(e));
+    if (const char* e = getenv("ZKE_W_GROUP")) c.group = (uint32_t)std::max(2, atoi(e));
+    return c;
+}
 MsmConfig msm_config_full(uint32_t n, bool precomputed) {
     MsmConfig c;
     c.c = n >= (1u << 18) ? 16 : (n >= (1u << 12) ? 12 : 8);
