@@ -207,3 +207,20 @@ def test_prove_bit_exact_sha256_block():
     r, s = 0x1111111111111111111111111111, 0x2222222222222222222222
     proofs, _, _ = ctx.prove(1, r.to_bytes(32, "little") + s.to_bytes(32, "little"))
     assert proofs == oracle_prove(c, sec, wt, r, s, threads=8)
+
+
+@pytest.mark.parametrize("levels", ["1", "2", "3"])
+def test_batched_affine_h_msm_bit_exact(levels, monkeypatch):
+    """The opt-in batched-affine bucket accumulation of the H multi-exponentiation (ZKE_H_BA, msm.cu:
+    ba_chunk_sum_kernel) must give the proof the XYZZ kernel and the CPU oracle give, bit for bit."""
+    from zkutil import oracle_prove, product_sections
+    monkeypatch.setenv("ZKE_H_BA", levels)
+    c = z.Circuit("Sha256Bytes", [64])
+    zk = z.Zkey(c, seed=3)
+    sec = product_sections(zk)
+    ctx = _ctx(c, zk)
+    padded, plen = z.sha256_pad(b"batched affine", 64)
+    wt, _ = ctx.witness(c.pack_inputs({"paddedIn": list(padded), "paddedInLength": plen}), 1)
+    r, s = 0x3333333333333333333333333333, 0x4444444444444444444444
+    proofs, _, _ = ctx.prove(1, r.to_bytes(32, "little") + s.to_bytes(32, "little"))
+    assert proofs == oracle_prove(c, sec, wt, r, s, threads=8)

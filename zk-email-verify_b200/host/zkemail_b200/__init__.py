@@ -11,3 +11,4 @@ from .input_generators import (generate_circuit_inputs, generate_email_verifier_
 from .engine import AssertFailed, Context, Zkey, device_count, proof_to_json, verify  # noqa: F401
 from .chunked_zkey import generate_proof, verify_proof, register_circuit, generateProof, verifyProof  # noqa: F401
 from . import synthetic  # noqa: F401,E402
+from . import iden3_binfile  # noqa: F401,E402
