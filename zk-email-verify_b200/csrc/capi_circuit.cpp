@@ -57,6 +57,13 @@ Circuit build_named(const std::string& name, const std::vector<int64_t>& p) {
         if (p.size() > 8) ep.public_pubkey = p[8] != 0;
         return build_email_verifier(ep);
     }
+    if (name == "TwitterVerifier") {          // Proof-of-Twitter: EmailVerifier(H, Bd, n, k, 0) + body regex + packing + address
+        need(4);
+        EmailVerifierParams ep;
+        ep.max_headers_length = (uint32_t)p[0]; ep.max_body_length = (uint32_t)p[1]; ep.n = (uint32_t)p[2]; ep.k = (uint32_t)p[3];
+        ep.twitter = true;
+        return build_email_verifier(ep);
+    }
     Builder b(name);
     ScopeGuard g(b, name);
     if (name == "Sha256Bytes") {              // test-circuits/sha-test.circom
@@ -99,6 +106,28 @@ Circuit build_named(const std::string& name, const std::vector<int64_t>& p) {
         auto out = b.declare_outputs("out", (nb + bpe - 1) / bpe);
         LCVec in = inputs(b, "in", nb);
         outputs(b, "out", pack_bits(b, in, bpe), out);
+    } else if (name == "PackBytes") {         // utils/bytes.circom:28-60
+        need(1);
+        uint32_t n = (uint32_t)p[0];
+        auto out = b.declare_outputs("out", (n + 30) / 31);
+        LCVec in = inputs(b, "in", n);
+        outputs(b, "out", pack_bytes(b, in), out);
+    } else if (name == "PackRegexReveal") {   // utils/regex.circom:61-77
+        need(2);
+        uint32_t n = (uint32_t)p[0], r = (uint32_t)p[1];
+        auto out = b.declare_outputs("out", (r + 30) / 31);
+        LCVec in = inputs(b, "in", n);
+        LC start = inputs(b, "startIndex", 1)[0];
+        outputs(b, "out", pack_regex_reveal(b, in, start, r), out);
+    } else if (name == "TwitterResetRegex") {
+        need(1);
+        uint32_t n = (uint32_t)p[0];
+        auto out = b.declare_outputs("out", 1);
+        auto rev = b.declare_outputs("reveal0", n);
+        LCVec msg = inputs(b, "msg", n);
+        LCVec r = twitter_reset_regex(b, msg);
+        b.assign_output(out[0], r[0]);
+        for (uint32_t i = 0; i < n; ++i) b.assign_output(rev[i], r[1 + i]);
     } else if (name == "ByteMask") {          // test-circuits/byte-mask-test.circom
         need(1);
         uint32_t n = (uint32_t)p[0];

@@ -273,6 +273,29 @@ LCVec pack_bits(Builder& b, const LCVec& in, uint32_t bpe) {
     return out;
 }
 
+LCVec pack_bytes(Builder& b, const LCVec& in) {
+    ScopeGuard g(b, "PackBytes");
+    const uint32_t pack_size = 31;                                      // MAX_BYTES_IN_FIELD (utils/constants.circom:13-15)
+    const uint32_t max_bytes = (uint32_t)in.size();
+    const uint32_t max_ints = (max_bytes + pack_size - 1) / pack_size;  // computeIntChunkLength (utils/bytes.circom:10-20)
+    LCVec out(max_ints);
+    for (uint32_t i = 0; i < max_ints; ++i) {
+        LC sum;                                                         // intSums[i][j] chain (:37-54)
+        for (uint32_t j = 0; j < pack_size; ++j) {
+            const uint32_t idx = pack_size * i + j;
+            if (idx >= max_bytes) break;                                // out of bounds: the previous value is carried
+            sum = j == 0 ? b.signal(in[idx]) : b.signal(sum + in[idx] * fr_pow2(8 * j));
+        }
+        out[i] = sum;
+    }
+    return out;
+}
+
+LCVec pack_regex_reveal(Builder& b, const LCVec& in, const LC& start_index, uint32_t max_reveal_len) {
+    ScopeGuard g(b, "PackRegexReveal");
+    return pack_bytes(b, select_regex_reveal(b, in, start_index, max_reveal_len));
+}
+
 LCVec byte_mask(Builder& b, const LCVec& in, const LCVec& mask) {
     ScopeGuard g(b, "ByteMask");
     LCVec out(in.size());
@@ -686,15 +709,19 @@ Circuit build_email_verifier(const EmailVerifierParams& P, bool materialize_line
     ScopeGuard g(b, "EmailVerifier");
 
     // outputs first (circom witness order)
+    if (P.twitter && P.ignore_body_hash_check) throw std::runtime_error("TwitterVerifier needs the body (ignoreBodyHashCheck = 0)");
     Var pubkey_hash = b.declare_outputs("pubkeyHash", 1)[0];
-    Var sha_hi = b.declare_outputs("shaHi", 1)[0];
-    Var sha_lo = b.declare_outputs("shaLo", 1)[0];
+    Var sha_hi = 0, sha_lo = 0, twitter_username = 0;
+    if (P.twitter) twitter_username = b.declare_outputs("twitterUsername", 1)[0];
+    else { sha_hi = b.declare_outputs("shaHi", 1)[0]; sha_lo = b.declare_outputs("shaLo", 1)[0]; }
     std::vector<Var> masked_header, masked_body;
     if (P.enable_header_masking) masked_header = b.declare_outputs("maskedHeader", H);
     if (!P.ignore_body_hash_check && P.enable_body_masking) masked_body = b.declare_outputs("maskedBody", Bd);
 
     auto to_lcs = [](const std::vector<Var>& v) { LCVec o(v.size()); for (size_t i = 0; i < v.size(); ++i) o[i] = LC(v[i]); return o; };
     std::vector<Var> pubkey_v;
+    LC twitter_address;
+    if (P.twitter) twitter_address = LC(b.declare_inputs("address", 1, true)[0]);   // component main { public [ address ] }
     if (P.public_pubkey) pubkey_v = b.declare_inputs("pubkey", k, true);
     LCVec email_header = to_lcs(b.declare_inputs("emailHeader", H, false));
     LC email_header_length = LC(b.declare_inputs("emailHeaderLength", 1, false)[0]);
@@ -711,13 +738,15 @@ Circuit build_email_verifier(const EmailVerifierParams& P, bool materialize_line
         if (P.remove_soft_line_breaks) decoded_in = to_lcs(b.declare_inputs("decodedEmailBodyIn", Bd, false));
         if (P.enable_body_masking) body_mask = to_lcs(b.declare_inputs("bodyMask", Bd, false));
     }
+    LC twitter_index;
+    if (P.twitter) twitter_index = LC(b.declare_inputs("twitterUsernameIndex", 1, false)[0]);
 
     num2bits(b, email_header_length, log2_ceil(H));                      // :58-59
     assert_zero_padding(b, email_header, email_header_length);           // :63
     LCVec sha = sha256_bytes(b, email_header, email_header_length);      // :67
     LCVec packed = pack_bits(b, sha, 128);                               // :68-71
-    b.assign_output(sha_hi, packed[0]);
-    b.assign_output(sha_lo, packed[1]);
+    if (P.twitter) { b.signal(packed[0]); b.signal(packed[1]); }          // EV.shaHi / EV.shaLo: signals of the sub-component
+    else { b.assign_output(sha_hi, packed[0]); b.assign_output(sha_lo, packed[1]); }
 
     const uint32_t rsa_message_size = (256 + n) / n;                     // :74-84
     LCVec rsa_message(k);
@@ -760,6 +789,15 @@ Circuit build_email_verifier(const EmailVerifierParams& P, bool materialize_line
         }
     }
     b.assign_output(pubkey_hash, poseidon_large(b, n, pubkey));          // :173
+    if (P.twitter) {
+        ScopeGuard tg(b, "TwitterVerifier");
+        LCVec rx = twitter_reset_regex(b, email_body);
+        b.enforce_eq(rx[0], one_lc());                                   // twitterFound === 1
+        LCVec reveal(rx.begin() + 1, rx.end());
+        LCVec packs = pack_regex_reveal(b, reveal, twitter_index, 21);   // maxTwitterUsernameLength = 21 -> one field element
+        b.assign_output(twitter_username, packs[0]);
+        (void)twitter_address;   // bound to the proof through its public-input row of the QAP
+    }
     return b.finalize();
 }
 

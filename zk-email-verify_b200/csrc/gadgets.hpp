@@ -40,6 +40,8 @@ LCVec var_shift_left(Builder& b, const LCVec& in, const LC& shift, uint32_t max_
 void assert_zero_padding(Builder& b, const LCVec& in, const LC& start_index);              // utils/array.circom:149-164
 LCVec pack_bits(Builder& b, const LCVec& in, uint32_t bits_per_element);    // utils/bytes.circom:194-210
 LCVec byte_mask(Builder& b, const LCVec& in, const LCVec& mask);            // utils/bytes.circom:173-185
+LCVec pack_bytes(Builder& b, const LCVec& in);                              // utils/bytes.circom:28-60 (31 bytes per field element, little-endian)
+LCVec pack_regex_reveal(Builder& b, const LCVec& in, const LC& start_index, uint32_t max_reveal_len);  // utils/regex.circom:61-77
 LCVec select_regex_reveal(Builder& b, const LCVec& in, const LC& start_index, uint32_t max_reveal_len);  // utils/regex.circom:17-52
 LC poseidon_large(Builder& b, uint32_t bits_per_chunk, const LCVec& in);    // utils/hash.circom:15-39
 LC poseidon_modular(Builder& b, const LCVec& in);                           // utils/hash.circom:49-83
@@ -64,6 +66,11 @@ LCVec base64_decode(Builder& b, uint32_t byte_length, const LCVec& in);     // l
 // ---- @zk-email/zk-regex-circom body_hash_regex (un-vendored; call site email-verifier.circom:126) ----
 // out[0] = match flag, out[1..] = reveal bytes (msg[i] inside the bh= value, else 0)
 LCVec body_hash_regex(Builder& b, const LCVec& msg);
+// zk-regex circuit of an arbitrary decomposed regex: parts = {(regex, is_public)...}; same output layout
+LCVec regex_match(Builder& b, const std::string& scope, const std::vector<std::pair<std::string, bool>>& parts, const LCVec& msg);
+// `email was meant for @(\w+)` with the user name public - the body regex of the Proof-of-Twitter circuit
+// (selector string: docs/zk-email-docs/UsageGuide/README.md:84; the circuit itself is not in the reference tree)
+LCVec twitter_reset_regex(Builder& b, const LCVec& msg);
 
 // ---- email-verifier.circom:42-174 ------------------------------------------------------------
 struct EmailVerifierParams {
@@ -71,6 +78,10 @@ struct EmailVerifierParams {
     bool ignore_body_hash_check = false, enable_header_masking = false, enable_body_masking = false;
     bool remove_soft_line_breaks = false;
     bool public_pubkey = false;   // `component main { public [pubkey] }` as in tests/test-circuits/email-verifier-test.circom:5
+    // Proof-of-Twitter wrapper (BASELINE configs[3]; public signals as in packages/rust-verifier/tests/data/
+    // proof_of_twitter/public.json: [pubkeyHash, twitterUsername, address]): EmailVerifier as a sub-component whose
+    // shaHi / shaLo stay internal, plus the body regex, PackRegexReveal(maxBodyLength, 21) and a public `address` input
+    bool twitter = false;
 };
 Circuit build_email_verifier(const EmailVerifierParams& p, bool materialize_linear = true);
 

@@ -334,5 +334,20 @@ LCVec body_hash_regex(Builder& b, const LCVec& msg) {
     return regex_circuit(b, dfa, msg);
 }
 
+LCVec regex_match(Builder& b, const std::string& scope, const std::vector<std::pair<std::string, bool>>& parts, const LCVec& msg) {
+    ScopeGuard g(b, scope.c_str());
+    const Dfa dfa = build_dfa(parts);
+    return regex_circuit(b, dfa, msg);
+}
+
+LCVec twitter_reset_regex(Builder& b, const LCVec& msg) {
+    ScopeGuard g(b, "TwitterResetRegex");
+    static const Dfa dfa = build_dfa({
+        {"email was meant for @", false},
+        {"[a-zA-Z0-9_]+", true},
+    });
+    return regex_circuit(b, dfa, msg);
+}
+
 }  // namespace gadgets
 }  // namespace zke

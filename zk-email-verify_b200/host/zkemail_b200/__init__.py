@@ -7,6 +7,7 @@ from .binary_format import (bigint_to_chunked_bytes, bytes_to_bigint, int64_to_b
 from .sha_utils import generate_partial_sha, partial_sha, sha256_pad, sha_hash  # noqa: F401
 from .dkim import DKIMVerificationResult, verify_dkim_signature  # noqa: F401
 from .input_generators import (generate_circuit_inputs, generate_email_verifier_inputs,  # noqa: F401
+                               generate_twitter_verifier_inputs_from_dkim_result,
                                generate_email_verifier_inputs_from_dkim_result)
 from .engine import AssertFailed, Context, Zkey, device_count, proof_to_json, verify  # noqa: F401
 from .chunked_zkey import generate_proof, verify_proof, register_circuit, generateProof, verifyProof  # noqa: F401

@@ -92,3 +92,25 @@ def generate_email_verifier_inputs(raw_email: bytes | str, input_params: dict | 
 
 # BASELINE.json's north_star uses the pre-rename name; keep it as an alias
 generate_circuit_inputs = generate_email_verifier_inputs
+
+
+TWITTER_SELECTOR = "email was meant for @"   # /root/reference/docs/zk-email-docs/UsageGuide/README.md:84
+
+
+def generate_twitter_verifier_inputs_from_dkim_result(dkim_result: DKIMVerificationResult, address: int | str,
+                                                      params: dict | None = None) -> dict:
+    """Inputs of the Proof-of-Twitter circuit (BASELINE configs[3]; `TwitterVerifier` in capi_circuit.cpp): the
+    EmailVerifier inputs with `shaPrecomputeSelector` = the Twitter selector (UsageGuide/README.md:84), plus
+    `twitterUsernameIndex` = position of the user name in the remaining body and the public `address`.  The reference
+    repo documents the selector and ships the resulting proof fixture; the generator script itself lives in the
+    (un-vendored) proof-of-twitter app."""
+    p = dict(params or {})
+    p.setdefault("shaPrecomputeSelector", TWITTER_SELECTOR)
+    inputs = generate_email_verifier_inputs_from_dkim_result(dkim_result, p)
+    body = bytes(int(x) for x in inputs["emailBody"])
+    at = body.find(TWITTER_SELECTOR.encode())
+    if at < 0:
+        raise ValueError(f'Sha precompute selector "{TWITTER_SELECTOR}" not found in the body')
+    inputs["twitterUsernameIndex"] = str(at + len(TWITTER_SELECTOR))
+    inputs["address"] = str(int(address, 0) if isinstance(address, str) else int(address))
+    return inputs
