@@ -507,13 +507,14 @@ MsmConfig msm_config_witness() {
 MsmConfig msm_config_full(uint32_t n, bool precomputed) {
     MsmConfig c;
     c.c = n >= (1u << 18) ? 16 : (n >= (1u << 12) ? 12 : 8);
-    c.chunk = 256; c.group = 16; c.classify = false; c.extra_passes = 0;
+    c.chunk = 256; c.group = n >= (1u << 20) ? 64 : 16; c.classify = false; c.extra_passes = 0;   // group 64: 46.2 vs 45.8 proofs/s at 2^22
     c.precomputed = precomputed;
     // Batched-affine bucket accumulation (ba.cuh) is an opt-in experiment: ZKE_H_BA=<levels> at key-setup time.
     // Measured on B200 at 2^22 points: 11.2 ms (2 levels) against 10.9 ms for the XYZZ kernel - it executes 15 % fewer
     // instructions but waits on its scratch traffic (27 GB of DRAM reads/writes, fmaheavy pipe 60 % busy instead of
     // 86 %), see profiles/ncu_r01_ba_summary.txt.
     if (const char* e = getenv("ZKE_H_BA")) c.ba_levels = precomputed ? std::max(0, std::min(3, atoi(e))) : 0;
+    if (const char* e = getenv("ZKE_H_GROUP")) c.group = (uint32_t)std::max(2, atoi(e));   // experiments
     if (c.ba_levels) c.chunk = 160;   // one chunk per bucket at the expected ~104 entries; sizes the batched-affine scratch rows
     if (precomputed) {
         // one shared bucket set of 2^(c-1) buckets: pick c so that the buckets (~ n * W / 2^(c-1) entries each) still
