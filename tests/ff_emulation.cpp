@@ -15,6 +15,9 @@ static void run(int which, const uint32_t* a, const uint32_t* b, uint32_t* out) 
         case 3: { uint32_t T[16]; Fr::sqr_wide(T, x.v); z = Fr::redc_wide(T); break; }
         case 4: z = x + y; break;
         case 5: z = x - y; break;
+        case 8: z = Fr::sqr_cios(x); break;
+        case 6: z = Fr::mul_add2(x, y, y, x + y); break;          // x*y + y*(x+y)
+        case 7: z = Fr::mul_sub2(x, y, y, x + y); break;          // x*y - y*(x+y)
         default: z = x;
     }
     memcpy(out, z.v, 32);

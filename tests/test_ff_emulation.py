@@ -36,19 +36,28 @@ def _check(mod, name):
     for _ in range(200):
         h = random.randrange(1<<128); A.append((h | (h << 128)) % mod); B.append(random.randrange(mod))
         A.append(random.randrange(mod)); l = random.randrange(1<<125); B.append(l | (l<<128))
+    A += [mod - 1, mod - 1, mod - 2, mod - 1]; B += [mod - 1, mod - 2, mod - 1, (mod - 1) // 2]   # largest sums of products
     n = len(A)
     a, b = arr(A), arr(B)
     Rinv = pow(R, -1, mod)
-    for which, nm in [(0,'mul_cios'),(1,'mul_sos(karatsuba)'),(2,'mul_sos_plain'),(3,'sqr')]:
+    for which, nm in [(0,'mul_cios'),(1,'mul_sos(karatsuba)'),(2,'mul_sos_plain'),(3,'sqr'),(8,'sqr_cios')]:
         out = (ctypes.c_uint32 * (8*n))()
         lib.ff_op(which, a, b, out, n)
         got = unarr(out, 8, n)
         bad = 0
         for i in range(n):
-            exp = (A[i]*B[i]*Rinv) % mod if which != 3 else (A[i]*A[i]*Rinv) % mod
+            exp = (A[i]*B[i]*Rinv) % mod if which not in (3, 8) else (A[i]*A[i]*Rinv) % mod
             if got[i] != exp:
                 bad += 1
                 if bad < 3: print(name, nm, 'MISMATCH', i, hex(A[i]), hex(B[i]), hex(got[i]), hex(exp))
+        assert not bad, "%s %s: %d/%d wrong" % (name, nm, bad, n)
+    for which, nm, f in [(4, 'add', lambda x, y: (x + y) % mod), (5, 'sub', lambda x, y: (x - y) % mod),
+                         (6, 'mul_add2', lambda x, y: (x * y + y * ((x + y) % mod)) * Rinv % mod),
+                         (7, 'mul_sub2', lambda x, y: (x * y - y * ((x + y) % mod)) * Rinv % mod)]:
+        out = (ctypes.c_uint32 * (8*n))()
+        lib.ff_op(which, a, b, out, n)
+        got = unarr(out, 8, n)
+        bad = sum(1 for i in range(n) if got[i] != f(A[i], B[i]))
         assert not bad, "%s %s: %d/%d wrong" % (name, nm, bad, n)
     for which, nm in [(0,'mul_wide8'),(1,'karatsuba'),(2,'sqr_wide')]:
         out = (ctypes.c_uint32 * (16*n))()

@@ -10,6 +10,17 @@
 namespace zke {
 namespace dev {
 
+// a*b - c*d: one interleaved dual product for the prime field (ff.cuh: mul_add2), two products otherwise
+template <class Tag>
+__device__ __forceinline__ Fp<Tag> mul_sub2(const Fp<Tag>& a, const Fp<Tag>& b, const Fp<Tag>& c, const Fp<Tag>& d) {
+#ifdef ZKE_NO_DUAL_PRODUCT
+    return a * b - c * d;
+#else
+    return Fp<Tag>::mul_sub2(a, b, c, d);
+#endif
+}
+__device__ __forceinline__ Fq2 mul_sub2(const Fq2& a, const Fq2& b, const Fq2& c, const Fq2& d) { return a * b - c * d; }
+
 template <class F>
 struct Affine {
     F x, y;
@@ -49,7 +60,7 @@ struct XYZZ {
         F X2 = x.sqr();
         F M = X2.dbl() + X2;
         F X3 = M.sqr() - S.dbl();
-        F Y3 = M * (S - X3) - W * y;
+        F Y3 = mul_sub2(M, S - X3, W, y);
         zz = V * zz;
         zzz = W * zzz;
         x = X3; y = Y3;
@@ -73,7 +84,7 @@ struct XYZZ {
         F PPP = P * PP;
         F Q = x * PP;
         F X3 = R.sqr() - PPP - Q.dbl();
-        F Y3 = R * (Q - X3) - y * PPP;
+        F Y3 = mul_sub2(R, Q - X3, y, PPP);
         zz = zz * PP;
         zzz = zzz * PPP;
         x = X3; y = Y3;
@@ -98,7 +109,7 @@ struct XYZZ {
         F PPP = P * PP;
         F Q = U1 * PP;
         F X3 = R.sqr() - PPP - Q.dbl();
-        F Y3 = R * (Q - X3) - S1 * PPP;
+        F Y3 = mul_sub2(R, Q - X3, S1, PPP);
         zz = zz * o.zz * PP;
         zzz = zzz * o.zzz * PPP;
         x = X3; y = Y3;

@@ -237,6 +237,117 @@ struct Fp {
         return r;
     }
 
+    // ---- interleaved square: a^2 = sum_i a_i B^i (a_i B^i + 2 a_{>i}), i.e. row i only multiplies a_i with limb i of a
+    // and the limbs above i of 2a - 36 instead of 64 multiply IMAD.WIDE (the 72 of the reduction rows stay).  2a < 2^255
+    // fits 8 limbs because p < 2^254; limb i + 1 of 2 a_{>i} is limb i + 1 of 2a with the bit shifted in from a_i
+    // cleared.  Pairs below the row index are skipped at compile time (the shifted vector still takes its carry).
+    template <int I>
+    static __device__ __forceinline__ uint32_t sqr_limb(const uint32_t* a, const uint32_t* a2, int j) {
+        return j == I ? a[j] : (j == I + 1 ? (a2[j] & ~1u) : a2[j]);
+    }
+    template <int I, bool FIRST>
+    static __device__ __forceinline__ void sqr_n_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, const uint32_t* a2) {
+        const FieldConsts& C = Tag::C();
+        const uint32_t bi = a[I];
+        if (FIRST) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) pair_mul(odd[j], odd[j + 1], sqr_limb<I>(a, a2, j + 1), bi);
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) pair_mul(even[j], even[j + 1], sqr_limb<I>(a, a2, j), bi);
+        } else {
+            even[0] = add_cc(even[0], odd[1]);
+            // shifted vector: pair t takes multiplicand limb 2t + 1
+#pragma unroll
+            for (int j = 0; j < 6; j += 2) {
+                if (j + 1 >= I) pair_madc_cc_from(odd[j], odd[j + 1], sqr_limb<I>(a, a2, j + 1), bi, odd[j + 2], odd[j + 3]);
+                else { odd[j] = addc_cc(odd[j + 2], 0); odd[j + 1] = addc_cc(odd[j + 3], 0); }
+            }
+            pair_madc_last(odd[6], odd[7], sqr_limb<I>(a, a2, 7), bi);     // limb 7 >= I always
+            // unshifted vector: pair t takes multiplicand limb 2t; pairs below the row index are untouched
+            bool live = false;
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                if (j >= I) {
+                    if (live) pair_madc_cc(even[j], even[j + 1], sqr_limb<I>(a, a2, j), bi);
+                    else pair_mad_cc(even[j], even[j + 1], sqr_limb<I>(a, a2, j), bi);
+                    live = true;
+                }
+            }
+            odd[7] = live ? addc(odd[7], 0) : odd[7];
+        }
+        const uint32_t mi = even[0] * C.inv;
+        cmad_n(odd, C.mod + 1, mi);
+        cmad_n(even, C.mod, mi);
+        odd[7] = addc(odd[7], 0);
+    }
+    static __device__ __forceinline__ Fp sqr_cios(const Fp& x) {
+        uint32_t a2[8], even[8], odd[8];
+        const uint32_t* a = x.v;
+        a2[0] = a[0] << 1;
+#pragma unroll
+        for (int j = 1; j < 8; ++j) a2[j] = (a[j] << 1) | (a[j - 1] >> 31);
+        sqr_n_redc<0, true>(even, odd, a, a2);
+        sqr_n_redc<1, false>(odd, even, a, a2);
+        sqr_n_redc<2, false>(even, odd, a, a2);
+        sqr_n_redc<3, false>(odd, even, a, a2);
+        sqr_n_redc<4, false>(even, odd, a, a2);
+        sqr_n_redc<5, false>(odd, even, a, a2);
+        sqr_n_redc<6, false>(even, odd, a, a2);
+        sqr_n_redc<7, false>(odd, even, a, a2);
+        Fp r;
+        r.v[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int k = 1; k < 7; ++k) r.v[k] = addc_cc(even[k], odd[k + 1]);
+        r.v[7] = addc(even[7], 0);
+        r.reduce_once();
+        return r;
+    }
+
+    // (a*b + c*d) / 2^256 mod p in ONE interleaved pass: every row adds both partial products before its reduction row,
+    // so the sum costs 64 + 64 + 72 = 200 IMAD.WIDE instead of 2 x 136 and needs no wide intermediate.  Operands must
+    // be fully reduced (< p < 2^254): three 30-bit top-limb products then still fit the top accumulator limb.
+    // Used where the curve formulas have a difference of two products (Y3 = R (Q - X3) - Y1 PPP).
+    template <bool FIRST>
+    static __device__ __forceinline__ void mad2_n_redc(uint32_t* even, uint32_t* odd, const uint32_t* a, uint32_t bi,
+                                                       const uint32_t* c, uint32_t di) {
+        const FieldConsts& C = Tag::C();
+        if (FIRST) {
+            mul_n(odd, a + 1, bi);
+            mul_n(even, a, bi);
+        } else {
+            even[0] = add_cc(even[0], odd[1]);
+            madc_n_rshift(odd, a + 1, bi);
+            cmad_n(even, a, bi);
+            odd[7] = addc(odd[7], 0);
+        }
+        cmad_n(odd, c + 1, di);
+        cmad_n(even, c, di);
+        odd[7] = addc(odd[7], 0);
+        const uint32_t mi = even[0] * C.inv;
+        cmad_n(odd, C.mod + 1, mi);
+        cmad_n(even, C.mod, mi);
+        odd[7] = addc(odd[7], 0);
+    }
+    static __device__ __forceinline__ Fp mul_add2(const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+        uint32_t even[8], odd[8];
+        mad2_n_redc<true>(even, odd, a.v, b.v[0], c.v, d.v[0]);
+        mad2_n_redc<false>(odd, even, a.v, b.v[1], c.v, d.v[1]);
+#pragma unroll
+        for (int i = 2; i < 8; i += 2) {
+            mad2_n_redc<false>(even, odd, a.v, b.v[i], c.v, d.v[i]);
+            mad2_n_redc<false>(odd, even, a.v, b.v[i + 1], c.v, d.v[i + 1]);
+        }
+        Fp r;
+        r.v[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int k = 1; k < 7; ++k) r.v[k] = addc_cc(even[k], odd[k + 1]);
+        r.v[7] = addc(even[7], 0);
+        r.reduce_once();      // (ab + cd + m p) / R < p (2p / R + 1) < 1.4 p
+        return r;
+    }
+    // a*b - c*d (Montgomery), via the negated second factor
+    static __device__ __forceinline__ Fp mul_sub2(const Fp& a, const Fp& b, const Fp& c, const Fp& d) { return mul_add2(a, b, c.neg(), d); }
+
     // One reduction row (a "multiplication by 1" row of the interleaved product): the running total loses its lowest
     // limb (made zero by adding mi * p) and is implicitly divided by 2^32; the roles of the two vectors swap.
     template <bool FIRST>
@@ -435,8 +546,10 @@ struct Fp {
         uint32_t T[16];
         sqr_wide(T, v);
         return redc_wide(T);
-#else
+#elif defined(ZKE_FP_SQR_MUL)
         return mul_cios(*this, *this);
+#else
+        return sqr_cios(*this);
 #endif
     }
     __device__ __forceinline__ Fp to_mont() const { return *this * r2(); }
