@@ -255,25 +255,38 @@ __global__ void __launch_bounds__(128, MINB)
 chunk_sum_kernel(const uint8_t* __restrict__ points, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
                  const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off, const uint32_t* __restrict__ work_bucket,
                  uint32_t n_buckets, uint32_t CHUNK, uint8_t* partial) {
-    __shared__ uint32_t s_cnt[128], s_w[128];
+    // GROUP consecutive blocks rank the same GROUP x 128 chunks and each takes one slice of 128 consecutive ranks: the
+    // 32 chunks of a warp then span 1 / (4 GROUP) of the size distribution (gridDim.x is a multiple of GROUP)
+    constexpr uint32_t GROUP = 4, SORT = GROUP * 128;
+    __shared__ uint32_t s_cnt[SORT], s_w[128];
     const uint32_t total = chunk_off[n_buckets];
     const uint32_t tid = threadIdx.x;
-    for (uint32_t base = blockIdx.x * 128u; base < total; base += gridDim.x * 128u) {
-        const uint32_t w0 = base + tid;
-        uint32_t cnt0 = 0;
-        if (w0 < total) {
-            const uint32_t b0 = work_bucket[w0];
-            cnt0 = min(CHUNK, hist[b0] - (w0 - chunk_off[b0]) * CHUNK);
+    const uint32_t slice = blockIdx.x % GROUP;
+    for (uint32_t base = (blockIdx.x / GROUP) * SORT; base < total; base += (gridDim.x / GROUP) * SORT) {
+        uint32_t cnt0[GROUP];
+#pragma unroll
+        for (uint32_t q = 0; q < GROUP; ++q) {
+            const uint32_t w0 = base + q * 128u + tid;
+            cnt0[q] = 0;
+            if (w0 < total) {
+                const uint32_t b0 = work_bucket[w0];
+                cnt0[q] = min(CHUNK, hist[b0] - (w0 - chunk_off[b0]) * CHUNK);
+            }
+            s_cnt[q * 128u + tid] = cnt0[q];
         }
-        s_cnt[tid] = cnt0;
         __syncthreads();
-        uint32_t rank = 0;
-#pragma unroll 8
-        for (uint32_t j = 0; j < 128; ++j) {
+        uint32_t rank[GROUP];
+#pragma unroll
+        for (uint32_t q = 0; q < GROUP; ++q) rank[q] = 0;
+#pragma unroll 4
+        for (uint32_t j = 0; j < SORT; ++j) {
             const uint32_t cj = s_cnt[j];
-            rank += (cj > cnt0) || (cj == cnt0 && j < tid);
+#pragma unroll
+            for (uint32_t q = 0; q < GROUP; ++q) rank[q] += (cj > cnt0[q]) || (cj == cnt0[q] && j < q * 128u + tid);
         }
-        s_w[rank] = w0;
+#pragma unroll
+        for (uint32_t q = 0; q < GROUP; ++q)
+            if (rank[q] / 128u == slice) s_w[rank[q] % 128u] = base + q * 128u + tid;
         __syncthreads();
         const uint32_t w = s_w[tid];
         if (w < total) {
