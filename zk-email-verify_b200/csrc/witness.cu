@@ -98,16 +98,6 @@ __device__ void fpmul_hint_dev(const DevProgram& P, uint8_t* w, uint32_t aux_off
     }
 }
 
-// Stores a witness value and asks for its sector back in L1: global stores do not allocate in L1, so without the hint
-// the consumers of the next level (same SM - one CTA per email) pay an L2 round trip for a value this SM just produced.
-// ZKE_WITNESS_NO_WARM compiles the hint out.
-__device__ __forceinline__ void store_warm(const Fr& x, uint8_t* p) {
-    x.store(p);
-#ifndef ZKE_WITNESS_NO_WARM
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p) : "memory");
-#endif
-}
-
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -172,11 +162,11 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
                     xa = (xa * xb) * Fr::r2() + xc;
                 }
             }
-            store_warm(xa, w + 32ull * op.x);
+            xa.store(w + 32ull * op.x);
         } else if (code == 2) {   // OP_SHRAND
-            store_warm(shrand(Fr::load(w + 32ull * op.z), op.w & 0xffffu, op.w >> 16), w + 32ull * op.x);
+            shrand(Fr::load(w + 32ull * op.z), op.w & 0xffffu, op.w >> 16).store(w + 32ull * op.x);
         } else if (code == 3) {   // OP_INVZ
-            store_warm(invz(P, Fr::load(w + 32ull * op.z)), w + 32ull * op.x);
+            invz(P, Fr::load(w + 32ull * op.z)).store(w + 32ull * op.x);
         } else if (code == 4) {   // OP_FPMUL
             fpmul_hint_dev(P, w, op.z, op.x);
         }
