@@ -244,64 +244,64 @@ static __global__ void fill_work_kernel(const uint32_t* __restrict__ hist, const
     for (uint32_t i = 0; i < nch; ++i) work_bucket[chunk_off[b] + i] = b;
 }
 
-// one thread per chunk: partial[w] = sum of (+/-) points of the chunk.
-// Bucket sizes are Poisson distributed (104 +- 10 entries for the H points), and a warp runs as long as its largest
+// ---------------------------------------------------------------- chunk order (counting sort by size)
+// Bucket sizes are Poisson distributed (104 +- 10 entries for the H points) and a warp runs as long as its largest
 // chunk: with chunks taken in index order only 26 of 32 lanes are active on average (ncu: 26.1 threads per
-// instruction).  Each block therefore sorts its 128 chunks by size (rank by counting in shared memory, ~400
-// instructions per thread against ~270 k of additions) and hands them out in that order, so the 32 chunks of a warp
-// have nearly equal lengths.
+// instruction).  The chunks are therefore counting-sorted by size, largest first: `order[t]` is the chunk thread t
+// works on, so the 32 lanes of a warp - and the 4 warps of a block - get chunks of (nearly) equal length, and the
+// longest chunks start first.  Two small kernels around the existing exclusive scan: per-block histograms stored
+// bin-major (mat[bin][block]) so that ONE flat scan yields every block's write offset for every size.
+static const int ORDER_BLOCK = 256;
+__device__ __forceinline__ uint32_t chunk_size_of(uint32_t w, const uint32_t* hist, const uint32_t* chunk_off, const uint32_t* work_bucket, uint32_t CHUNK) {
+    const uint32_t b = work_bucket[w];
+    return min(CHUNK, hist[b] - (w - chunk_off[b]) * CHUNK);
+}
+static __global__ void __launch_bounds__(ORDER_BLOCK)
+chunk_key_hist_kernel(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off, const uint32_t* __restrict__ work_bucket,
+                      uint32_t n_buckets, uint32_t CHUNK, uint32_t* mat) {
+    extern __shared__ uint32_t s_hist[];      // CHUNK bins: bin = CHUNK - size (size >= 1)
+    const uint32_t total = chunk_off[n_buckets];
+    for (uint32_t i = threadIdx.x; i < CHUNK; i += ORDER_BLOCK) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t w = blockIdx.x * ORDER_BLOCK + threadIdx.x;
+    if (w < total) atomicAdd(&s_hist[CHUNK - chunk_size_of(w, hist, chunk_off, work_bucket, CHUNK)], 1u);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < CHUNK; i += ORDER_BLOCK) mat[(size_t)i * gridDim.x + blockIdx.x] = s_hist[i];
+}
+static __global__ void __launch_bounds__(ORDER_BLOCK)
+chunk_order_kernel(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off, const uint32_t* __restrict__ work_bucket,
+                   uint32_t n_buckets, uint32_t CHUNK, const uint32_t* __restrict__ mat_off, uint32_t* order) {
+    __shared__ uint32_t s_key[ORDER_BLOCK];
+    const uint32_t total = chunk_off[n_buckets];
+    const uint32_t w = blockIdx.x * ORDER_BLOCK + threadIdx.x;
+    const uint32_t key = w < total ? CHUNK - chunk_size_of(w, hist, chunk_off, work_bucket, CHUNK) : 0xffffffffu;
+    s_key[threadIdx.x] = key;
+    __syncthreads();
+    if (w >= total) return;
+    uint32_t local = 0;
+    for (uint32_t j = 0; j < threadIdx.x; ++j) local += s_key[j] == key;
+    order[mat_off[(size_t)key * gridDim.x + blockIdx.x] + local] = w;
+}
+
+// one thread per chunk: partial[w] = sum of (+/-) points of chunk w = order[thread]
 template <class F, int MINB>
 __global__ void __launch_bounds__(128, MINB)
 chunk_sum_kernel(const uint8_t* __restrict__ points, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
                  const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off, const uint32_t* __restrict__ work_bucket,
-                 uint32_t n_buckets, uint32_t CHUNK, uint8_t* partial) {
-    // GROUP consecutive blocks rank the same GROUP x 128 chunks and each takes one slice of 128 consecutive ranks: the
-    // 32 chunks of a warp then span 1 / (4 GROUP) of the size distribution (gridDim.x is a multiple of GROUP)
-    constexpr uint32_t GROUP = 4, SORT = GROUP * 128;
-    __shared__ uint32_t s_cnt[SORT], s_w[128];
+                 const uint32_t* __restrict__ order, uint32_t n_buckets, uint32_t CHUNK, uint8_t* partial) {
     const uint32_t total = chunk_off[n_buckets];
-    const uint32_t tid = threadIdx.x;
-    const uint32_t slice = blockIdx.x % GROUP;
-    for (uint32_t base = (blockIdx.x / GROUP) * SORT; base < total; base += (gridDim.x / GROUP) * SORT) {
-        uint32_t cnt0[GROUP];
-#pragma unroll
-        for (uint32_t q = 0; q < GROUP; ++q) {
-            const uint32_t w0 = base + q * 128u + tid;
-            cnt0[q] = 0;
-            if (w0 < total) {
-                const uint32_t b0 = work_bucket[w0];
-                cnt0[q] = min(CHUNK, hist[b0] - (w0 - chunk_off[b0]) * CHUNK);
-            }
-            s_cnt[q * 128u + tid] = cnt0[q];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const uint32_t w = order[t];
+        const uint32_t b = work_bucket[w];
+        const uint32_t ci = w - chunk_off[b];
+        const uint32_t beg = offsets[b] + ci * CHUNK;
+        const uint32_t end = min(offsets[b] + hist[b], beg + CHUNK);
+        XYZZ<F> acc = XYZZ<F>::inf();
+        for (uint32_t k = beg; k < end; ++k) {
+            const uint32_t e = entries[k];
+            acc.madd(Affine<F>::load(points + sizeof(Affine<F>) * (size_t)(e & 0x7fffffffu)), (e >> 31) != 0);
         }
-        __syncthreads();
-        uint32_t rank[GROUP];
-#pragma unroll
-        for (uint32_t q = 0; q < GROUP; ++q) rank[q] = 0;
-#pragma unroll 4
-        for (uint32_t j = 0; j < SORT; ++j) {
-            const uint32_t cj = s_cnt[j];
-#pragma unroll
-            for (uint32_t q = 0; q < GROUP; ++q) rank[q] += (cj > cnt0[q]) || (cj == cnt0[q] && j < q * 128u + tid);
-        }
-#pragma unroll
-        for (uint32_t q = 0; q < GROUP; ++q)
-            if (rank[q] / 128u == slice) s_w[rank[q] % 128u] = base + q * 128u + tid;
-        __syncthreads();
-        const uint32_t w = s_w[tid];
-        if (w < total) {
-            const uint32_t b = work_bucket[w];
-            const uint32_t ci = w - chunk_off[b];
-            const uint32_t beg = offsets[b] + ci * CHUNK;
-            const uint32_t end = min(offsets[b] + hist[b], beg + CHUNK);
-            XYZZ<F> acc = XYZZ<F>::inf();
-            for (uint32_t k = beg; k < end; ++k) {
-                const uint32_t e = entries[k];
-                acc.madd(Affine<F>::load(points + sizeof(Affine<F>) * (size_t)(e & 0x7fffffffu)), (e >> 31) != 0);
-            }
-            acc.store(partial + sizeof(XYZZ<F>) * (size_t)w);
-        }
-        __syncthreads();
+        acc.store(partial + sizeof(XYZZ<F>) * (size_t)w);
     }
 }
 
@@ -592,6 +592,11 @@ size_t MsmPlan<F>::workspace_bytes(uint32_t n, const MsmConfig& cfg) {
     al(sizeof(XYZZ<F>) * groups);      // group sums
     al(sizeof(XYZZ<F>) * ((size_t)n / LIST_FANIN + 2) * 2);  // list reduction ping-pong
     if (cfg.ba_levels > 0 && sizeof(F) == 32) al(ba_scratch_bytes<F>(cfg.chunk, ba_cap(n_buckets, max_chunks)));
+    const size_t order_cells = ((max_chunks + ORDER_BLOCK - 1) / ORDER_BLOCK) * cfg.chunk;
+    al(4 * max_chunks);                       // order
+    al(4 * (order_cells + 1));                // per-block size histograms, bin-major
+    al(4 * (order_cells + 1));                // their exclusive scan
+    al(4 * (order_cells / SCAN_TILE + 2));    // scan tiles
     return b;
 }
 
@@ -633,6 +638,11 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     uint8_t* red_a = take(sizeof(XYZZ<F>) * list_slots);
     uint8_t* red_b = take(sizeof(XYZZ<F>) * list_slots);
     uint8_t* ba_scratch = (cfg.ba_levels > 0 && sizeof(F) == 32) ? take(ba_scratch_bytes<F>(cfg.chunk, ba_cap(n_buckets, max_chunks))) : nullptr;
+    const size_t order_cells = ((max_chunks + ORDER_BLOCK - 1) / ORDER_BLOCK) * cfg.chunk;
+    uint32_t* order = (uint32_t*)take(4 * max_chunks);
+    uint32_t* order_mat = (uint32_t*)take(4 * (order_cells + 1));
+    uint32_t* order_off = (uint32_t*)take(4 * (order_cells + 1));
+    uint32_t* order_tiles = (uint32_t*)take(4 * (order_cells / SCAN_TILE + 2));
 
     // result block: [MSM_ONES_SLOTS partial sums of the unit-scalar points][MSM_MAX_WINDOWS window sums]
     uint8_t* res_ones = result;
@@ -674,6 +684,13 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     digit_scatter_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, offsets, cursor, entries);
     exclusive_scan(hist, n_buckets, D.chunk, 0, chunk_off, tiles, st);
     fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, chunk_off, n_buckets, D.chunk, 0, work_bucket);
+    {   // order[] = chunks sorted by size, largest first
+        const uint32_t nblk = (uint32_t)((max_chunks + ORDER_BLOCK - 1) / ORDER_BLOCK);
+        chunk_key_hist_kernel<<<nblk, ORDER_BLOCK, 4 * D.chunk, st>>>(hist, chunk_off, work_bucket, n_buckets, D.chunk, order_mat);
+        exclusive_scan(order_mat, nblk * D.chunk, 0, 0, order_off, order_tiles, st);
+        chunk_order_kernel<<<nblk, ORDER_BLOCK, 0, st>>>(hist, chunk_off, work_bucket, n_buckets, D.chunk, order_off, order);
+        ZKE_COUNT_LAUNCH(2);
+    }
     cudaStream_t st_light = st;
     if (heavy && heavy->st != st) {
         cudaEventRecord(heavy->before, st);
@@ -692,9 +709,9 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
         if (cfg.ba_levels <= 0 || (D.chunk & 3) || sizeof(F) != 32) ba_levels = 0;   // scratch is only planned for ba_levels > 0; G1 only
         if (ba_levels > 0) launch_ba<F>(ba_levels, waves, points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial,
                                         ba_scratch, ba_cap(n_buckets, max_chunks), st);
-        else if (minb >= 6) chunk_sum_kernel<F, 6><<<148 * 6 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
-        else if (minb == 5) chunk_sum_kernel<F, 5><<<148 * 5 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
-        else chunk_sum_kernel<F, 4><<<148 * 4 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial);
+        else if (minb >= 6) chunk_sum_kernel<F, 6><<<148 * 6 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
+        else if (minb == 5) chunk_sum_kernel<F, 5><<<148 * 5 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
+        else chunk_sum_kernel<F, 4><<<148 * 4 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
     }
     if (ev) cudaEventRecord(ev[1], st);
     if (st != st_light) {
