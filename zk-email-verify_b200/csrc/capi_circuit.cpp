@@ -128,6 +128,43 @@ Circuit build_named(const std::string& name, const std::vector<int64_t>& p) {
         LCVec r = twitter_reset_regex(b, msg);
         b.assign_output(out[0], r[0]);
         for (uint32_t i = 0; i < n; ++i) b.assign_output(rev[i], r[1 + i]);
+    } else if (name == "SplitBytesToWords") { // test-circuits/split-bytes-to-words-test.circom
+        need(3);
+        auto out = b.declare_outputs("out", (uint32_t)p[2]);
+        LCVec in = inputs(b, "in", (uint32_t)p[0]);
+        outputs(b, "out", split_bytes_to_words(b, in, (uint32_t)p[1], (uint32_t)p[2]), out);
+    } else if (name == "CheckSubstringMatch") {   // test-circuits/check-substring-match-test.circom
+        need(1);
+        auto out = b.declare_outputs("isMatch", 1);
+        LCVec in = inputs(b, "in", (uint32_t)p[0]), sub = inputs(b, "substring", (uint32_t)p[0]);
+        outputs(b, "isMatch", {check_substring_match(b, in, sub)}, out);
+    } else if (name == "CountSubstringOccurrences") {   // test-circuits/count-substring-occurrences-test.circom
+        need(2);
+        auto out = b.declare_outputs("count", 1);
+        LCVec in = inputs(b, "in", (uint32_t)p[0]), sub = inputs(b, "substring", (uint32_t)p[1]);
+        outputs(b, "count", {count_substring_occurrences(b, in, sub)}, out);
+    } else if (name == "RevealSubstring") {   // test-circuits/reveal-substring-test.circom
+        need(3);
+        auto out = b.declare_outputs("substring", (uint32_t)p[1]);
+        LCVec in = inputs(b, "in", (uint32_t)p[0]);
+        LC start = inputs(b, "substringStartIndex", 1)[0], len = inputs(b, "substringLength", 1)[0];
+        outputs(b, "substring", reveal_substring(b, in, start, len, (uint32_t)p[1], p[2] != 0), out);
+    } else if (name == "SelectSubArray") {
+        need(2);
+        auto out = b.declare_outputs("out", (uint32_t)p[1]);
+        LCVec in = inputs(b, "in", (uint32_t)p[0]);
+        LC start = inputs(b, "startIndex", 1)[0], len = inputs(b, "length", 1)[0];
+        outputs(b, "out", select_sub_array(b, in, start, len, (uint32_t)p[1]), out);
+    } else if (name == "CleanEmailAddress") { // test-circuits/clean-email-address-test.circom
+        need(1);
+        auto out = b.declare_outputs("isValid", 1);
+        LCVec enc = inputs(b, "encoded", (uint32_t)p[0]), dec = inputs(b, "decoded", (uint32_t)p[0]);
+        outputs(b, "isValid", {clean_email_address(b, enc, dec)}, out);
+    } else if (name == "EmailNullifier") {    // helpers/email-nullifier.circom
+        need(2);
+        auto out = b.declare_outputs("out", 1);
+        LCVec sig = inputs(b, "signature", (uint32_t)p[1]);
+        outputs(b, "out", {email_nullifier(b, (uint32_t)p[0], sig)}, out);
     } else if (name == "ByteMask") {          // test-circuits/byte-mask-test.circom
         need(1);
         uint32_t n = (uint32_t)p[0];

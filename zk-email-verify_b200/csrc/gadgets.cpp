@@ -296,6 +296,125 @@ LCVec pack_regex_reveal(Builder& b, const LCVec& in, const LC& start_index, uint
     return pack_bytes(b, select_regex_reveal(b, in, start_index, max_reveal_len));
 }
 
+LCVec split_bytes_to_words(Builder& b, const LCVec& in, uint32_t n, uint32_t k) {
+    ScopeGuard g(b, "SplitBytesToWords");
+    const uint32_t l = (uint32_t)in.size();
+    std::vector<LCVec> bits(l);
+    for (uint32_t i = 0; i < l; ++i) bits[i] = num2bits(b, in[i], 8);            // :129-133
+    LCVec out(k);
+    for (uint32_t i = 0; i < k; ++i) {                                           // :134-148: word i = bits [i n, (i+1) n) of the
+        LCVec word(n);                                                           // big-endian byte string read as an integer
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint64_t pos = (uint64_t)i * n + j;
+            word[j] = pos >= 8ull * l ? LC() : bits[l - (uint32_t)(pos / 8) - 1][pos % 8];
+        }
+        out[i] = b.signal(bits2num(b, word));
+    }
+    return out;
+}
+
+// ---------------------------------------------------------------- utils/array.circom (add-on templates)
+LCVec select_sub_array(Builder& b, const LCVec& in, const LC& start_index, const LC& length, uint32_t max_sub_len) {
+    ScopeGuard g(b, "SelectSubArray");
+    if (max_sub_len >= in.size()) throw std::runtime_error("SelectSubArray: maxSubArrayLen >= maxArrayLen");   // :79
+    LCVec shifted = var_shift_left(b, in, start_index, max_sub_len);
+    const uint32_t bits = log2_ceil(max_sub_len);
+    LCVec out(max_sub_len);
+    for (uint32_t i = 0; i < max_sub_len; ++i)                                    // :90-97: zero from `length` on
+        out[i] = b.mul(greater_than(b, bits, length, const_u64(i)), shifted[i]);
+    return out;
+}
+
+LC check_substring_match(Builder& b, const LCVec& in, const LCVec& substring) {
+    ScopeGuard g(b, "CheckSubstringMatch");
+    const size_t n = substring.size();
+    b.enforce_eq(is_zero(b, substring[0]), LC());                                 // :199-201 firstElementNonZero === 0
+    LC acc = b.signal(one_lc());                                                  // matchAccumulator[0] <== 1
+    for (size_t i = 0; i < n; ++i) {
+        LC diff = b.mul(in[i] - substring[i], substring[i]);                      // :210 (zero where the pattern is zero-padded)
+        acc = b.mul(acc, is_zero(b, diff));                                       // :211-212
+    }
+    return acc;
+}
+
+LC count_substring_occurrences(Builder& b, const LCVec& in, const LCVec& substring) {
+    ScopeGuard g(b, "CountSubstringOccurrences");
+    const size_t max_len = in.size(), sub_len = substring.size();
+    if (max_len < sub_len) throw std::runtime_error("CountSubstringOccurrences: maxLen < maxSubstringLen");   // :227
+    LCVec matches(max_len);
+    for (size_t i = 0; i < max_len; ++i) {                                        // :234-246
+        LCVec window(sub_len);
+        for (size_t j = 0; j < sub_len; ++j) window[j] = i + j < max_len ? in[i + j] : LC();
+        matches[i] = check_substring_match(b, window, substring);
+    }
+    return calculate_total(b, matches);                                           // :248-253
+}
+
+// ---------------------------------------------------------------- helpers/reveal-substring.circom
+LCVec reveal_substring(Builder& b, const LCVec& in, const LC& start_index, const LC& length, uint32_t max_substring_len,
+                       bool check_uniqueness) {
+    ScopeGuard g(b, "RevealSubstring");
+    const uint32_t max_length = (uint32_t)in.size();
+    if (max_substring_len >= max_length) throw std::runtime_error("RevealSubstring: maxSubstringLength >= maxLength");   // :14
+    b.enforce_eq(less_than(b, log2_ceil(max_length), start_index, const_u64(max_length)), one_lc());                    // :23-24
+    b.enforce_eq(less_than(b, log2_ceil(max_substring_len + 1), length, const_u64(max_substring_len + 1)), one_lc());   // :27-28
+    LC sum = b.signal(start_index + length);                                                                            // :31
+    b.enforce_eq(less_than(b, log2_ceil(max_length + 1), sum, const_u64(max_length + 1)), one_lc());                     // :32-33
+    LCVec sub = select_sub_array(b, in, start_index, length, max_substring_len);                                        // :36-39
+    if (check_uniqueness) b.enforce_eq(count_substring_occurrences(b, in, sub), one_lc());                              // :41-47
+    return sub;
+}
+
+// ---------------------------------------------------------------- utils/email.circom
+LC clean_email_address(Builder& b, const LCVec& encoded, const LCVec& decoded) {
+    ScopeGuard g(b, "CleanEmailAddress");
+    const size_t n = encoded.size();
+    LCVec all(2 * n);
+    for (size_t i = 0; i < n; ++i) { all[i] = encoded[i]; all[n + i] = decoded[i]; }
+    LC r = b.signal(poseidon_modular(b, all));                                    // :45-52
+    LCVec is_plus(n), is_at(n), neither(n), local(n), should_remove(n);
+    for (size_t i = 0; i < n; ++i) {                                              // :54-66
+        is_plus[i] = is_equal(b, encoded[i], const_u64(43));
+        is_at[i] = is_equal(b, encoded[i], const_u64(64));
+        neither[i] = b.mul(one_lc() - is_plus[i], one_lc() - is_at[i]);
+        local[i] = i == 0 ? b.signal(neither[0]) : b.mul(local[i - 1], neither[i]);
+    }
+    LCVec local_period(n);
+    for (size_t i = 0; i < n; ++i) local_period[i] = b.mul(local[i], is_equal(b, encoded[i], const_u64(46)));   // :69-72
+    LC found_plus = b.signal(is_plus[0]);                                         // :75-78 (running count, not used further)
+    for (size_t i = 1; i < n; ++i) found_plus = b.signal(found_plus + is_plus[i]);
+    LCVec after_plus(n), after_at(n);
+    after_plus[0] = b.signal(one_lc() - is_plus[0]);                              // :81-84
+    for (size_t i = 1; i < n; ++i) after_plus[i] = b.mul(after_plus[i - 1], one_lc() - is_plus[i]);
+    LC has_alias = b.signal(one_lc() - after_plus[n - 1]);                        // :85
+    after_at[0] = b.signal(one_lc() - is_at[0]);                                  // :87-90
+    for (size_t i = 1; i < n; ++i) after_at[i] = b.mul(after_at[i - 1], one_lc() - is_at[i]);
+    for (size_t i = 0; i < n; ++i) {                                              // :92-100
+        LC in_alias = b.mul(has_alias, b.signal(after_at[i] - after_plus[i]));
+        should_remove[i] = b.signal(local_period[i] + in_alias);
+    }
+    LCVec processed(n), r_enc(n), r_dec(n);
+    for (size_t i = 0; i < n; ++i) processed[i] = b.mul(one_lc() - should_remove[i], encoded[i]);   // :103-105
+    for (size_t i = 0; i < n; ++i) {                                              // :108-120 Mux1: out = (c1 - c0) s + c0
+        LC c0 = i == 0 ? r : b.mul(r_enc[i - 1], r);
+        LC c1 = i == 0 ? one_lc() : r_enc[i - 1];
+        r_enc[i] = b.mul_add(c1 - c0, should_remove[i], c0);
+    }
+    r_dec[0] = r;                                                                 // :123-126
+    for (size_t i = 1; i < n; ++i) r_dec[i] = b.mul(r_dec[i - 1], r);
+    LC sum_enc, sum_dec;
+    for (size_t i = 0; i < n; ++i) sum_enc = i == 0 ? b.mul(r_enc[0], processed[0]) : b.mul_add(r_enc[i], processed[i], sum_enc);   // :129-132
+    for (size_t i = 0; i < n; ++i) sum_dec = i == 0 ? b.mul(r_dec[0], decoded[0]) : b.mul_add(r_dec[i], decoded[i], sum_dec);      // :135-138
+    return is_equal(b, sum_enc, sum_dec);                                         // :141
+}
+
+// ---------------------------------------------------------------- helpers/email-nullifier.circom
+LC email_nullifier(Builder& b, uint32_t bits_per_chunk, const LCVec& signature) {
+    ScopeGuard g(b, "EmailNullifier");
+    LC sig_hash = b.signal(poseidon_large(b, bits_per_chunk, signature));         // :20
+    return poseidon(b, LCVec{sig_hash});                                          // :22
+}
+
 LCVec byte_mask(Builder& b, const LCVec& in, const LCVec& mask) {
     ScopeGuard g(b, "ByteMask");
     LCVec out(in.size());

@@ -42,6 +42,14 @@ LCVec pack_bits(Builder& b, const LCVec& in, uint32_t bits_per_element);    // u
 LCVec byte_mask(Builder& b, const LCVec& in, const LCVec& mask);            // utils/bytes.circom:173-185
 LCVec pack_bytes(Builder& b, const LCVec& in);                              // utils/bytes.circom:28-60 (31 bytes per field element, little-endian)
 LCVec pack_regex_reveal(Builder& b, const LCVec& in, const LC& start_index, uint32_t max_reveal_len);  // utils/regex.circom:61-77
+LCVec split_bytes_to_words(Builder& b, const LCVec& in, uint32_t n, uint32_t k);          // utils/bytes.circom:125-149
+LCVec select_sub_array(Builder& b, const LCVec& in, const LC& start_index, const LC& length, uint32_t max_sub_len);  // utils/array.circom:78-98
+LC check_substring_match(Builder& b, const LCVec& in, const LCVec& substring);             // utils/array.circom:193-217
+LC count_substring_occurrences(Builder& b, const LCVec& in, const LCVec& substring);       // utils/array.circom:226-253
+LCVec reveal_substring(Builder& b, const LCVec& in, const LC& start_index, const LC& length, uint32_t max_substring_len,
+                       bool check_uniqueness);                                             // helpers/reveal-substring.circom:13-49
+LC clean_email_address(Builder& b, const LCVec& encoded, const LCVec& decoded);            // utils/email.circom:16-139 (returns isValid)
+LC email_nullifier(Builder& b, uint32_t bits_per_chunk, const LCVec& signature);           // helpers/email-nullifier.circom:14-23
 LCVec select_regex_reveal(Builder& b, const LCVec& in, const LC& start_index, uint32_t max_reveal_len);  // utils/regex.circom:17-52
 LC poseidon_large(Builder& b, uint32_t bits_per_chunk, const LCVec& in);    // utils/hash.circom:15-39
 LC poseidon_modular(Builder& b, const LCVec& in);                           // utils/hash.circom:49-83
