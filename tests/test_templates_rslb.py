@@ -53,3 +53,30 @@ def test_email_verifier_with_soft_line_breaks():
     bad["decodedEmailBodyIn"] = dec
     with pytest.raises(AssertFailed):
         oracle_witness(c, bad)
+
+
+def test_email_verifier_with_qp_encoded_sha_precompute_selector():
+    """email-verifier-with-qp-encoded-sha-precompute-selector.test.ts:34-49: the SHA precompute selector is given in
+    decoded form while the body carries a quoted-printable soft line break inside it; the generator has to locate it in
+    the encoded body (input-generators.ts: getAdjustedSelector) and the circuit (removeSoftLineBreaks = 1) accepts.
+    The reference uses lorem_ipsum.eml, whose DKIM key needs DNS - a synthetic email of the same shape stands in."""
+    import zkemail_b200 as z
+    from zkemail_b200.synthetic import make_signed_email
+    c = Circuit("EmailVerifier", [640, 1408, 121, 17, 0, 0, 0, 1, 1])
+    key = z.synthetic.generate_key()
+    filler = b"".join(b"Lorem ipsum dolor sit amet, consectetur adipiscing elit %03d.\r\n" % i for i in range(14))
+    tail = b"Sed id imperdiet ne=\r\nque. Vivamus vel turpis non elit placerat feugiat ac a =\r\nmassa, and the rest of the body follows here.\r\n"
+    body = filler + tail
+    email = make_signed_email(11, key, body_len=len(body), body_override=body)
+    dk = z.verify_dkim_signature(email, resolver=lambda n, t: [z.synthetic.key_record(key)])
+    params = {"maxHeadersLength": 640, "maxBodyLength": 1408, "ignoreBodyHashCheck": False,
+              "removeSoftLineBreaks": True, "shaPrecomputeSelector": "imperdiet neque."}
+    inputs = z.generate_email_verifier_inputs_from_dkim_result(dk, params)
+    remaining = bytes(int(x) for x in inputs["emailBody"])
+    assert b"imperdiet ne=\r\nque." in remaining and len(remaining) == 1408
+    assert int(inputs["emailBodyLength"]) < len(body) + 72          # a whole number of 64-byte blocks was hashed on the host
+    assert bytes(int(x) for x in inputs["decodedEmailBodyIn"]).find(b"imperdiet neque.") >= 0
+    oracle_witness(c, inputs)                                        # calculateWitness + checkConstraints
+    with pytest.raises(Exception) as ei:
+        z.generate_email_verifier_inputs_from_dkim_result(dk, dict(params, shaPrecomputeSelector="not in the body"))
+    assert "not found in cleaned body" in str(ei.value)          # input-generators.ts:62
