@@ -247,7 +247,7 @@ def main():
                 "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "peak_source": peak_kind, "traffic": traffic, "kernel_ms": kernel_ms, "algorithmic_bytes": alg_bytes,
                 "note": "bound by the integer multiply pipe, not HBM: 13 windows x ~10 Fq products per 64-byte point "
-                        "(fmaheavy pipe 86 % busy in the ncu capture); traffic = 13 table levels gathered at 64 B per "
+                        "(fmaheavy pipe 85 % busy in the ncu capture); traffic = 13 table levels gathered at 64 B per "
                         "entry, see DESIGN.md section 5"}
     stages = {k: (v["ms"] / max(1, v["count"])) for k, v in prof.items()}
 
