@@ -168,9 +168,13 @@ int zkref_witness(const zkref_circuit* C, const uint8_t* inputs, uint8_t* w_byte
                 f_add(&ZK_FR, &w[dst], &t, &z);
                 break;
             }
-            case 2: { /* OP_SHRAND: (in >> b) & (2^c - 1) - circomlib Num2Bits `out[i] <-- (in >> i) & 1`,
+            case 2:   /* OP_SHRAND: (in >> b) & (2^c - 1) - circomlib Num2Bits `out[i] <-- (in >> i) & 1`,
                          lib/sha.circom:111 `inBlockIndex <-- (paddedInLength >> 9)` */
-                fe x = w[a], o = {{0, 0, 0, 0}};
+            case 5: { /* OP_SHRLC: the same hint applied to a linear combination (the front-end's fusion of the
+                         preceding partial-sum op, e.g. circomlib BinSum `out[k] <-- (lin >> k) & 1`) */
+                fe x, o = {{0, 0, 0, 0}};
+                if (code == 5) eval_lc(coef_r, C->lc_ptr, C->lc_var, C->lc_coef, a, w, &x);
+                else x = w[a];
                 unsigned ws = b >> 6, bs = b & 63;
                 for (unsigned j = 0; j + ws < 4; ++j) {
                     o.v[j] = x.v[j + ws] >> bs;

@@ -61,6 +61,8 @@ enum OpCode : uint32_t {
     OP_INVZ = 3,    // dst = val[a] == 0 ? 0 : 1 / val[a]
     OP_FPMUL = 4,   // big-integer hint of FpMul: aux[a..] = {n, k, a_vars[k], b_vars[k], p_vars[k]};
                     // dst..dst+k-1 = q limbs, dst+k..dst+2k-1 = r limbs where a*b = q*p + r, 0 <= r < p
+    OP_SHRLC = 5,   // dst = (lc[a] >> b) & (2^c - 1): OP_SHRAND fused with the OP_LIN that fed it through a scratch slot
+                    // (finalize(); one dependency level less per bit decomposition of a sum - SHA-256 adders)
 };
 struct WOp {
     uint32_t code;
@@ -136,6 +138,8 @@ class Builder {
     void pop_scope();
 
     bool materialize_linear = true;  // circom --O1 behaviour; false ~ --O2 (linear signals substituted)
+    bool fuse_shrand = default_fuse_shrand();   // OP_SHRLC fusion in finalize() (ZKE_FUSED_SHRAND)
+    static bool default_fuse_shrand();
 
     Circuit finalize();
 

@@ -305,7 +305,7 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                 if (o.code == OP_INVZ) return 1ull << 62;
                 if (o.code == OP_SHRAND) return 0;
                 const uint32_t ids[3] = {o.a, o.b, o.c};
-                const uint32_t n_lc = o.code == OP_LIN ? 1 : 3;
+                const uint32_t n_lc = o.code == OP_QUAD ? 3 : 1;
                 uint64_t mask = 0;
                 uint32_t pos = 0;
                 for (uint32_t q = 0; q < n_lc; ++q) {
@@ -326,9 +326,9 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                     if (base + t < order.size()) {
                         const WOp& o = c.ops[order[base + t]];
                         rec[0] = o.dst;
-                        if (o.code == OP_LIN || o.code == OP_QUAD) {
+                        if (o.code == OP_LIN || o.code == OP_QUAD || o.code == OP_SHRLC) {
                             const uint32_t ids[3] = {o.a, o.b, o.c};
-                            const uint32_t n_lc = o.code == OP_LIN ? 1 : 3;
+                            const uint32_t n_lc = o.code == OP_QUAD ? 3 : 1;
                             uint32_t n[3] = {0, 0, 0};
                             rec[2] = (uint32_t)(terms.size() / 2);
                             for (uint32_t q = 0; q < n_lc; ++q) {
@@ -339,6 +339,10 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                                         if (((coef_word[c.lc_coef[k]] >> 24) >= 2) == (pass == 0)) { terms.push_back(c.lc_var[k]); terms.push_back(coef_word[c.lc_coef[k]]); }
                             }
                             rec[1] = o.code | (n[0] << 8) | (n[1] << 13) | (n[2] << 18);
+                            if (o.code == OP_SHRLC) {
+                                if (o.b > 0xffffu || o.c > 0xffffu) throw std::runtime_error("OP_SHRLC operand out of range");
+                                rec[3] = o.b | (o.c << 16);
+                            }
                         } else if (o.code == OP_SHRAND) {
                             if (o.b > 0xffffu || o.c > 0xffffu) throw std::runtime_error("OP_SHRAND operand out of range");
                             rec[1] = o.code; rec[2] = o.a; rec[3] = o.b | (o.c << 16);

@@ -144,7 +144,7 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
             stage_terms(P, term_buf + ((k + 1) & 1) * WITNESS_TERM_BUF, hdr_next);
         }
         const uint32_t code = op.y & 0xffu;
-        if (code <= 1) {   // OP_LIN: dst = A ; OP_QUAD: dst = A*B + C (standard form in/out: two Montgomery products)
+        if (code <= 1 || code == 5) {   // OP_LIN: dst = A ; OP_QUAD: dst = A*B + C ; OP_SHRLC: dst = (A >> shift) & mask
             const uint32_t nA = (op.y >> 8) & 31u, nB = (op.y >> 13) & 31u, nC = (op.y >> 18) & 31u;
             const uint2* t = hdr.y > WITNESS_TERM_BUF ? P.terms + op.z : term_buf + (k & 1) * WITNESS_TERM_BUF + (op.z - hdr.x);
             Fr xa, xb, xc;
@@ -162,6 +162,7 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
                     xa = (xa * xb) * Fr::r2() + xc;
                 }
             }
+            if (code == 5) xa = shrand(xa, op.w & 0xffffu, op.w >> 16);
             xa.store(w + 32ull * op.x);
         } else if (code == 2) {   // OP_SHRAND
             shrand(Fr::load(w + 32ull * op.z), op.w & 0xffffu, op.w >> 16).store(w + 32ull * op.x);
