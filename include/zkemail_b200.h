@@ -44,6 +44,12 @@ typedef struct zke_ctx zke_ctx;         /* circuit + zkey resident on one GPU, w
  * ------------------------------------------------------------------------------------------------- */
 zke_circuit* zke_circuit_build(const char* template_name, const int64_t* params, size_t n_params,
                                char* err, size_t errcap);
+/* zk-regex circuit of an arbitrary decomposed regex (the generator behind BodyHashRegex; un-vendored
+ * @zk-email/zk-regex-circom, call site /root/reference/packages/circuits/email-verifier.circom:5,126):
+ * `parts[i]` is a regex fragment, `is_public[i]` != 0 marks the fragment whose matched bytes are revealed.
+ * Signals: input msg[msg_len], outputs out (match flag) and reveal0[msg_len]. */
+zke_circuit* zke_circuit_build_regex(const char* const* parts, const uint8_t* is_public, size_t n_parts, uint32_t msg_len,
+                                     char* err, size_t errcap);
 void zke_circuit_free(zke_circuit* c);
 
 typedef struct zke_circuit_info {
@@ -91,6 +97,21 @@ const char* zke_circuit_scope_name(const zke_circuit* c, uint32_t scope_index);
  * ~5m + N fixed-base scalar multiplications on GPU `device`; the key stays resident on that GPU.
  * ------------------------------------------------------------------------------------------------- */
 zke_zkey* zke_setup(const zke_circuit* c, uint64_t seed, int device, char* err, size_t errcap);
+/* Real proving keys: an iden3 `.zkey` (Groth16, BN254) as produced by `snarkjs groth16 setup` / `zkey contribute` -
+ * the third argument of snarkjs.groth16.fullProve(input, wasm, zkey)
+ * (/root/reference/packages/helpers/src/chunked-zkey.ts:80-84) and the first of `snarkjs groth16 prove zkey wtns`
+ * (/root/reference/docs/zk-email-docs/UsageGuide/README.md:139-195).  Sections 2-9 are validated (field moduli, every
+ * point on its curve) and made resident on GPU `device`: points as they are stored (affine, Montgomery), the A / B
+ * coefficient matrices of section 4 as CSR, the H points with their fixed-base table.
+ * zke_zkey_load_chunks takes the fork's chunked form: chunk i holds section i + 1, i.e. the files `${name}.zkeyb` ..
+ * `${name}.zkeyk` (chunked-zkey.ts:9,35-37); n_chunks >= 9 (section 10, the contribution log, is not needed). */
+zke_zkey* zke_zkey_load(const void* zkey_bytes, size_t len, int device, char* err, size_t errcap);
+zke_zkey* zke_zkey_load_chunks(const void* const* chunks, const size_t* lens, size_t n_chunks, int device, char* err, size_t errcap);
+/* Writes the key as a `.zkey` file image.  `c` supplies the coefficient section for keys made by zke_setup (pass NULL
+ * for loaded keys, which carry their own).  out == NULL: returns the size needed; < 0 on error. */
+int64_t zke_zkey_write(const zke_zkey* z, const zke_circuit* c, uint8_t* out, size_t cap);
+/* 1 if the key came from zke_setup (toxic waste known - anyone can forge proofs for it), 0 for a loaded key. */
+int zke_zkey_is_toy(const zke_zkey* z);
 void zke_zkey_free(zke_zkey* z);
 int zke_zkey_info(const zke_zkey* z, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_log2);
 /* zkey sections (iden3 .zkey numbering where one exists: 3 IC, 5 A, 6 B1, 7 B2, 8 C/"L", 9 H; header points apart). */
@@ -108,6 +129,8 @@ int64_t zke_zkey_section(const zke_zkey* z, int section, uint8_t* out, size_t ca
  * Contexts: circuit (+ optional proving key) resident on one GPU with work buffers for `max_batch` emails.
  * One host thread per context (or external locking).  All calls are synchronous at the ABI.
  * ------------------------------------------------------------------------------------------------- */
+/* `c` may be NULL when the key was loaded from a `.zkey`: such a context proves externally computed witnesses
+ * (zke_load_witness / zke_wtns_prove + zke_prove) from the key's own coefficient matrices. */
 zke_ctx* zke_ctx_open(const zke_circuit* c, const zke_zkey* zkey_or_null, int device, uint32_t max_batch,
                       char* err, size_t errcap);
 void zke_ctx_close(zke_ctx* x);
@@ -154,6 +177,17 @@ int zke_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs_out, 
 int zke_fullprove(zke_ctx* x, const uint8_t* inputs, size_t batch, const uint8_t* rs, uint8_t* proofs_out,
                   uint8_t* publics_out, int32_t* status, char* err, size_t errcap);
 
+/* Pipelined form of zke_fullprove: _submit enqueues the H2D copy, the witness kernel and all proving kernels of one
+ * batch and returns; _collect waits for the oldest submitted batch, finishes its proofs on the host and returns them.
+ * Up to two batches may be in flight, so the (latency-bound) witness kernel of batch k + 1 runs under the proving
+ * kernels of batch k.  zke_fullprove == submit + collect.  Returns as zke_fullprove. */
+int zke_fullprove_submit(zke_ctx* x, const uint8_t* inputs, size_t batch, const uint8_t* rs, char* err, size_t errcap);
+int zke_fullprove_collect(zke_ctx* x, uint8_t* proofs_out, uint8_t* publics_out, int32_t* status, char* err, size_t errcap);
+/* `snarkjs groth16 prove <zkey> <wtns>` (/root/reference/docs/zk-email-docs/UsageGuide/README.md:139-195): one iden3
+ * `.wtns` file image in, proof + public signals out. */
+int zke_wtns_prove(zke_ctx* x, const void* wtns_bytes, size_t len, const uint8_t* rs, uint8_t* proof_out, uint8_t* publics_out,
+                   char* err, size_t errcap);
+
 /* ---------------------------------------------------------------------------------------------------
  * JSON faces of the boundary (snarkjs file formats; shapes as in
  * /root/reference/packages/rust-verifier/tests/data/proof_of_twitter/{vkey,proof,public}.json).
@@ -161,8 +195,12 @@ int zke_fullprove(zke_ctx* x, const uint8_t* inputs, size_t batch, const uint8_t
  * ------------------------------------------------------------------------------------------------- */
 /* snarkjs.groth16.verify(vkey, publicSignals, proof): 1 valid, 0 invalid, < 0 malformed input.  Host only. */
 int zke_verify_json(const char* vkey_json, const char* public_json, const char* proof_json, char* err, size_t errcap);
-/* `snarkjs zkey export verificationkey` (vk_alphabeta_12 omitted: neither verifier needs it). */
+/* `snarkjs zkey export verificationkey`, incl. vk_alphabeta_12 = e(alpha_1, beta_2) in snarkjs' Fq12 tower layout
+ * (/root/reference/packages/rust-verifier/tests/data/proof_of_twitter/vkey.json:43). */
 int zke_zkey_vkey_json(const zke_zkey* z, char* out, size_t* len);
+/* e(alpha_1, beta_2) as snarkjs exports it: 12 x 32 bytes = vk_alphabeta_12[i][j][k] flattened, standard form LE.
+ * alpha: x, y; beta: x.c0, x.c1, y.c0, y.c1 (standard form LE).  Host only. */
+int zke_pairing_alphabeta(const uint8_t* alpha64, const uint8_t* beta128, uint8_t* out384);
 /* zke_prove output -> proof.json / public.json */
 int zke_proof_to_json(const uint8_t* proof256, const uint8_t* publics, uint32_t n_public, char* proof_json, size_t* proof_len,
                       char* public_json, size_t* public_len);

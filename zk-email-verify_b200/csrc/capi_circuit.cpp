@@ -268,6 +268,33 @@ zke_circuit* zke_circuit_build(const char* template_name, const int64_t* params,
     }
 }
 
+zke_circuit* zke_circuit_build_regex(const char* const* parts, const uint8_t* is_public, size_t n_parts, uint32_t msg_len,
+                                     char* err, size_t errcap) {
+    try {
+        if (!parts || !is_public || n_parts == 0) throw std::runtime_error("no regex parts given");
+        if (msg_len == 0 || msg_len > (1u << 16)) throw std::runtime_error("msg_len out of range");
+        std::vector<std::pair<std::string, bool>> pv;
+        for (size_t i = 0; i < n_parts; ++i) {
+            if (!parts[i]) throw std::runtime_error("null regex part");
+            pv.emplace_back(parts[i], is_public[i] != 0);
+        }
+        Builder b("Regex");
+        ScopeGuard g(b, "Regex");
+        auto out = b.declare_outputs("out", 1);
+        auto rev = b.declare_outputs("reveal0", msg_len);
+        LCVec msg = inputs(b, "msg", msg_len);
+        LCVec r = regex_match(b, "Regex", pv, msg);
+        b.assign_output(out[0], r[0]);
+        for (uint32_t i = 0; i < msg_len; ++i) b.assign_output(rev[i], r[1 + i]);
+        zke_circuit* c = new zke_circuit();
+        c->c = b.finalize();
+        return c;
+    } catch (const std::exception& e) {
+        set_err(err, errcap, e.what());
+        return nullptr;
+    }
+}
+
 void zke_circuit_free(zke_circuit* c) { delete c; }
 
 int zke_circuit_get_info(const zke_circuit* c, zke_circuit_info* o) {

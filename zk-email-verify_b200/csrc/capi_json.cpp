@@ -202,6 +202,25 @@ int zke_verify_json(const char* vkey_json, const char* public_json, const char* 
     } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
 }
 
+/* e(alpha_1, beta_2) in snarkjs' vk_alphabeta_12 layout; points and result in standard form, little-endian */
+int zke_pairing_alphabeta(const uint8_t* alpha64, const uint8_t* beta128, uint8_t* out384) {
+    try {
+        if (!alpha64 || !beta128 || !out384) return -1;
+        for (int i = 0; i < 6; ++i) {
+            U256 v;
+            memcpy(v.v, (i < 2 ? alpha64 : beta128 - 64) + 32 * i, 32);
+            if (u256_cmp(v, fq_params().p) >= 0) return -1;
+        }
+        G1AffineH a{fq_le(alpha64), fq_le(alpha64 + 32)};
+        G2AffineH b{Fq2{fq_le(beta128), fq_le(beta128 + 32)}, Fq2{fq_le(beta128 + 64), fq_le(beta128 + 96)}};
+        if (!g1_on_curve(a) || !g2_on_curve(b) || !g2_in_subgroup(b)) return -1;
+        U256 ab[12];
+        pairing_alphabeta(a, b, ab);
+        for (int i = 0; i < 12; ++i) memcpy(out384 + 32 * i, ab[i].v, 32);
+        return 0;
+    } catch (const std::exception&) { return -1; }
+}
+
 /* proofs as produced by zke_prove: 8 x 32 bytes; publics: n_public x 32 bytes -> snarkjs proof.json / public.json */
 int zke_proof_to_json(const uint8_t* proof256, const uint8_t* publics, uint32_t n_public, char* proof_json, size_t* proof_len,
                       char* public_json, size_t* public_len) {
@@ -243,6 +262,18 @@ int zke_zkey_vkey_json(const zke_zkey* z, char* out, size_t* len) {
         s += ",\"vk_beta_2\":" + g2_json(g2sec(ZKE_SEC_BETA2));
         s += ",\"vk_gamma_2\":" + g2_json(g2sec(ZKE_SEC_GAMMA2));
         s += ",\"vk_delta_2\":" + g2_json(g2sec(ZKE_SEC_DELTA2));
+        {
+            U256 ab[12];
+            pairing_alphabeta(g1sec(ZKE_SEC_ALPHA1, 1)[0], g2sec(ZKE_SEC_BETA2), ab);
+            s += ",\"vk_alphabeta_12\":[";
+            for (int i = 0; i < 2; ++i) {
+                s += i ? ",[" : "[";
+                for (int j = 0; j < 3; ++j)
+                    s += std::string(j ? "," : "") + "[\"" + u256_to_dec(ab[(i * 3 + j) * 2]) + "\",\"" + u256_to_dec(ab[(i * 3 + j) * 2 + 1]) + "\"]";
+                s += "]";
+            }
+            s += "]";
+        }
         s += ",\"IC\":[";
         auto ic = g1sec(ZKE_SEC_IC, n_public + 1);
         for (size_t i = 0; i < ic.size(); ++i) s += (i ? "," : "") + g1_json(ic[i]);

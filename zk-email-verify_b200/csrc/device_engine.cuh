@@ -47,6 +47,7 @@ struct DevR1cs {
 
 void upload_field_constants();
 
+cudaError_t configure_witness_kernel();   // once per device, before the first launch_witness on it
 void launch_witness(const DevProgram& P, uint8_t* w_all, size_t stride_elems, const uint8_t* inputs, uint32_t batch, cudaStream_t st);
 
 // a[i] = <A_i, w>, b[i] = <B_i, w> in Montgomery form for i < n_constraints, the n_public + 1 extra rows of the
@@ -54,6 +55,9 @@ void launch_witness(const DevProgram& P, uint8_t* w_all, size_t stride_elems, co
 // smallest violated row in *first_bad (initialised to 0xffffffff by the caller).
 // c_out (optional): a_i * b_i in Montgomery form (fused Hadamard product).  R1CS term words use the encoding of
 // lc_term.cuh.
+// flag[0] = 1 if any of the n 32-byte values is >= r, flag[1] = 1 if some witness (stride_elems apart) has w[0] != 1
+void launch_check_witness(const uint8_t* w_all, size_t stride_elems, uint32_t n_vars, uint32_t batch, uint32_t* flag, cudaStream_t st);
+
 void launch_build_ab(const DevR1cs& R, const uint8_t* w, uint8_t* a_out, uint8_t* b_out, uint8_t* c_out, uint32_t n, uint32_t* first_bad, cudaStream_t st);
 
 }  // namespace dev

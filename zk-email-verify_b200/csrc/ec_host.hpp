@@ -146,5 +146,7 @@ struct Proof {
     G2AffineH b;
 };
 bool groth16_verify(const VerifyingKey& vk, const std::vector<U256>& publics, const Proof& pr);
+bool g2_in_subgroup(const G2AffineH& p);
+void pairing_alphabeta(const G1AffineH& alpha1, const G2AffineH& beta2, U256 out[12]);   // snarkjs vk_alphabeta_12, [i][j][k] flattened
 
 }  // namespace zke

@@ -22,8 +22,11 @@ cudaError_t upload_constants_fixed_base(const FieldConsts*, const FieldConsts*);
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <memory>
+#include <mutex>
 #include <thread>
+#include <unordered_map>
 
 using namespace zke;
 
@@ -63,7 +66,11 @@ void select_device(int device) {
     CUDA_OK(dev::upload_constants_msm_g1(&fr, &fq));
     CUDA_OK(dev::upload_constants_msm_g2(&fr, &fq));
     CUDA_OK(dev::upload_constants_fixed_base(&fr, &fq));
+    CUDA_OK(dev::configure_witness_kernel());   // per-device function attribute (> 48 KB dynamic shared memory)
 }
+
+// launch-configuration errors are not sticky: pick them up right after the launches of a stage
+#define CHECK_LAUNCH() CUDA_OK(cudaGetLastError())
 
 // 32 x 256 window table of multiples of a generator, affine Montgomery, entry d = 0 is infinity
 template <class F>
@@ -96,20 +103,27 @@ std::vector<U256> to_standard(const std::vector<Fr>& v) {
 struct zke_zkey {
     uint32_t n_vars = 0, n_public = 0, log_n = 0;
     int device = 0;
+    bool toy = false;         // made by zke_setup: the toxic waste is known
     G1AffineH alpha1, beta1, delta1;
     G2AffineH beta2, gamma2, delta2;
     std::vector<G1AffineH> ic;
     DevBuf A, B1, B2, C, H;   // affine Montgomery points on the device; H holds h_levels window levels [level][N]
     int h_levels = 1;         // > 1: level j = 2^(c j) * H (fixed-base table for the H multi-exponentiation)
     dev::MsmConfig cfg_h;
+    // Coefficient matrices of `.zkey` section 4 (loaded keys only): A and B of the QAP as CSR over the 2^log_n domain
+    // rows, including the n_public + 1 extra rows of A; `coefs` is the interned coefficient table in standard form.
+    bool has_coefs = false;
+    std::vector<uint32_t> a_ptr, a_var, a_coef, b_ptr, b_var, b_coef;
+    std::vector<U256> coefs;
 };
 
 struct zke_ctx {
-    const zke_circuit* circuit = nullptr;
+    const zke_circuit* circuit = nullptr;   // may be null for a context opened from a loaded `.zkey` alone
     const zke_zkey* zkey = nullptr;
     int device = 0;
     uint32_t max_batch = 0;
-    cudaStream_t stream = nullptr;
+    uint32_t n_vars = 0, n_public = 0, n_inputs = 0;
+    cudaStream_t stream = nullptr;          // witness stream (highest priority)
     // circuit on device
     DevBuf ops, iter_hdr, lc_terms, aux, coef_r, small_inv;
     std::vector<uint32_t> coef_word;   // per interned coefficient: index | k << 16 | kind << 24 (lc_term.cuh)
@@ -120,9 +134,25 @@ struct zke_ctx {
     // ntt
     DevBuf tw_fwd, tw_inv, coset_scale;
     dev::NttTables ntt;
-    // work buffers
     size_t stride = 0;           // witness elements per email (n_vars + n_temps)
-    DevBuf w_all, inputs, results, first_bad;
+    DevBuf inputs, check_flag;   // inputs made resident by zke_upload_inputs; flag words of the witness validation
+    uint32_t inputs_resident = 0;
+    // Batch slots.  The synchronous entry points use slot 0; zke_fullprove_submit alternates between the two, so that
+    // the witness kernel of one batch (latency-bound, a few CTAs) runs while the proving kernels of the previous batch
+    // saturate the multiplier pipe.  Slot 1 is allocated on first use.
+    struct Slot {
+        bool allocated = false, busy = false;
+        DevBuf w_all, inputs, results, first_bad;
+        uint8_t* results_host = nullptr;      // pinned, [max_batch][ZKE_RESULT_STRIDE]
+        uint8_t* publics_host = nullptr;      // pinned, [max_batch][n_public][32]
+        std::vector<cudaEvent_t> done;        // per email
+        cudaEvent_t witness_done = nullptr;
+        uint32_t loaded = 0;                  // witnesses resident in w_all
+        uint32_t batch = 0;                   // batch of the pending submission
+        std::vector<uint8_t> rs;              // its blinding scalars ([batch][2][32]) or empty
+    };
+    Slot slots[2];
+    uint64_t n_submitted = 0, n_collected = 0;
     // proving lanes: emails are dealt round-robin to `n_lanes` streams, each with its own NTT vectors and MSM
     // workspace, so that the latency-bound tails of one email's kernels overlap the saturating kernels of another
     // Each lane owns two streams: `st` (high priority) carries the latency- / memory-bound kernels, `heavy` (low
@@ -132,14 +162,9 @@ struct zke_ctx {
     struct Lane { cudaStream_t st = nullptr, heavy = nullptr; cudaEvent_t ev[6] = {}; DevBuf va, vb, vc, vd, msm_ws; };
     Lane lanes[ZKE_MAX_LANES];
     int n_lanes = 1, lanes_alloc = 0;
-    uint8_t* results_host = nullptr;      // pinned, [max_batch][ZKE_RESULT_STRIDE]
-    uint8_t* publics_host = nullptr;      // pinned, [max_batch][n_public][32]
-    std::vector<cudaEvent_t> done;        // per email
-    cudaEvent_t witness_done = nullptr;
+    int finish_threads = 4;      // host threads that finish the MSMs / assemble the proofs (ZKE_FINISH_THREADS)
     dev::MsmConfig cfg_w, cfg_h;
     bool split_streams = true;   // ZKE_SPLIT_STREAMS=0: everything of a lane on one stream (experiments)
-    uint32_t loaded = 0;         // number of witnesses currently resident
-    uint32_t inputs_resident = 0; // batch size of the inputs currently in `inputs`
     std::vector<uint32_t> bad_host;
     // optional stage profiling (CUDA events on `stream`)
     bool profile = false;
@@ -166,6 +191,30 @@ struct zke_ctx {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ H table
+// zk->H holds level 0 (the N points of `.zkey` section 9) in its first N entries and is sized for h_levels levels:
+// level j = 2^(c j) * level 0, the fixed-base table that lets all windows of the H multi-exponentiation share one
+// bucket set (msm.cuh).
+static const uint32_t SETUP_SLAB = 1u << 20;
+static void h_table_config(zke_zkey* zk, size_t N) {
+    const char* e = getenv("ZKE_H_PRECOMP");
+    const bool precomp = !(e && atoi(e) == 0);
+    zk->cfg_h = dev::msm_config_full((uint32_t)N, precomp);
+    zk->h_levels = precomp ? dev::msm_windows(zk->cfg_h) : 1;
+}
+static void build_h_levels(zke_zkey* zk, size_t N, uint8_t* scratch, cudaStream_t st) {
+    for (int lvl = 1; lvl < zk->h_levels; ++lvl) {
+        const uint8_t* prev = zk->H.p + (size_t)(lvl - 1) * N * sizeof(dev::G1Affine);
+        uint8_t* cur = zk->H.p + (size_t)lvl * N * sizeof(dev::G1Affine);
+        for (size_t off = 0; off < N; off += SETUP_SLAB) {
+            uint32_t cnt = (uint32_t)std::min<size_t>(SETUP_SLAB, N - off);
+            dev::scale_pow2_batch<dev::Fq>(prev + sizeof(dev::G1Affine) * off, cnt, zk->cfg_h.c, scratch, cur + sizeof(dev::G1Affine) * off, st);
+        }
+    }
+    CHECK_LAUNCH();
+    CUDA_OK(cudaStreamSynchronize(st));
+}
+
 // ------------------------------------------------------------------------------------------------ setup
 static zke_zkey* do_setup(const zke_circuit* zc, uint64_t seed, int device) {
     select_device(device);
@@ -173,6 +222,7 @@ static zke_zkey* do_setup(const zke_circuit* zc, uint64_t seed, int device) {
     SetupScalars S = compute_setup_scalars(c, seed);
     std::unique_ptr<zke_zkey> zk(new zke_zkey());
     zk->n_vars = c.n_vars; zk->n_public = c.n_public(); zk->log_n = S.log_n; zk->device = device;
+    zk->toy = true;
     const size_t N = (size_t)1 << S.log_n;
     const uint32_t m = c.n_vars, l = c.n_public();
 
@@ -188,7 +238,7 @@ static zke_zkey* do_setup(const zke_circuit* zc, uint64_t seed, int device) {
     DevBuf t1, t2, scal, scratch;
     t1.upload(window_table<Fq>(g1_generator()));
     t2.upload(window_table<Fq2>(g2_generator()));
-    const uint32_t SLAB = 1u << 20;
+    const uint32_t SLAB = SETUP_SLAB;
     scratch.alloc((size_t)SLAB * sizeof(dev::G2XYZZ));
     cudaStream_t st = nullptr;
 
@@ -200,6 +250,7 @@ static zke_zkey* do_setup(const zke_circuit* zc, uint64_t seed, int device) {
             uint32_t cnt = (uint32_t)std::min<size_t>(SLAB, s.size() - off);
             dev::fixed_base_batch<dev::Fq>(t1.p, scal.p + 32 * off, cnt, scratch.p, out.p + sizeof(dev::G1Affine) * off, st);
         }
+        CHECK_LAUNCH();
         CUDA_OK(cudaStreamSynchronize(st));
     };
     run_g1(S.a, zk->A);
@@ -207,10 +258,7 @@ static zke_zkey* do_setup(const zke_circuit* zc, uint64_t seed, int device) {
     run_g1(S.kc, zk->C);
     {
         // H points, then (unless ZKE_H_PRECOMP=0) the fixed-base table levels 2^(c j) * H_i
-        const char* e = getenv("ZKE_H_PRECOMP");
-        const bool precomp = !(e && atoi(e) == 0);
-        zk->cfg_h = dev::msm_config_full((uint32_t)N, precomp);
-        zk->h_levels = precomp ? dev::msm_windows(zk->cfg_h) : 1;
+        h_table_config(zk.get(), N);
         std::vector<U256> std_s = to_standard(S.h);
         scal.upload(std_s);
         zk->H.alloc((size_t)zk->h_levels * N * sizeof(dev::G1Affine));
@@ -218,15 +266,7 @@ static zke_zkey* do_setup(const zke_circuit* zc, uint64_t seed, int device) {
             uint32_t cnt = (uint32_t)std::min<size_t>(SLAB, N - off);
             dev::fixed_base_batch<dev::Fq>(t1.p, scal.p + 32 * off, cnt, scratch.p, zk->H.p + sizeof(dev::G1Affine) * off, st);
         }
-        for (int lvl = 1; lvl < zk->h_levels; ++lvl) {
-            const uint8_t* prev = zk->H.p + (size_t)(lvl - 1) * N * sizeof(dev::G1Affine);
-            uint8_t* cur = zk->H.p + (size_t)lvl * N * sizeof(dev::G1Affine);
-            for (size_t off = 0; off < N; off += SLAB) {
-                uint32_t cnt = (uint32_t)std::min<size_t>(SLAB, N - off);
-                dev::scale_pow2_batch<dev::Fq>(prev + sizeof(dev::G1Affine) * off, cnt, zk->cfg_h.c, scratch.p, cur + sizeof(dev::G1Affine) * off, st);
-            }
-        }
-        CUDA_OK(cudaStreamSynchronize(st));
+        build_h_levels(zk.get(), N, scratch.p, st);
     }
     {
         std::vector<U256> std_s = to_standard(S.b);
@@ -236,30 +276,311 @@ static zke_zkey* do_setup(const zke_circuit* zc, uint64_t seed, int device) {
             uint32_t cnt = (uint32_t)std::min<size_t>(SLAB, m - off);
             dev::fixed_base_batch<dev::Fq2>(t2.p, scal.p + 32 * off, cnt, scratch.p, zk->B2.p + sizeof(dev::G2Affine) * off, st);
         }
+        CHECK_LAUNCH();
         CUDA_OK(cudaStreamSynchronize(st));
     }
     // IC = first l+1 entries of the kc points; they are not part of the C ("L") section
     zk->ic.resize(l + 1);
     CUDA_OK(cudaMemcpy(zk->ic.data(), zk->C.p, sizeof(G1AffineH) * (l + 1), cudaMemcpyDeviceToHost));
     CUDA_OK(cudaMemset(zk->C.p, 0, sizeof(G1AffineH) * (l + 1)));
-    (void)N;
     return zk.release();
 }
 
+// ------------------------------------------------------------------------------------------------ .zkey reader
+// iden3 binfile container: magic[4], u32 version, u32 nSections, then {u32 type, u64 size, payload} per section.
+// zkey v1 (Groth16): 1 {u32 protocol = 1}; 2 {n8q, q, n8r, r, nVars, nPublic, domainSize, alpha1, beta1, beta2, gamma2,
+// delta1, delta2}; 3 IC; 4 {u32 n, (u32 matrix, u32 constraint, u32 signal, value[n8r]) x n}; 5 A; 6 B1; 7 B2;
+// 8 C (private signals only); 9 H; 10 contributions.  Points are affine with Montgomery-form little-endian
+// coordinates (G2: x.c0, x.c1, y.c0, y.c1), infinity = all-zero bytes - the device image of this engine, so the point
+// sections are uploaded as they are; coefficient values are stored multiplied by R^2 (snarkjs multiplies them with
+// the raw witness in Montgomery arithmetic twice).  The formats live in the un-vendored @iden3/binfileutils /
+// snarkjs 0.5.0; the call sites are chunked-zkey.ts:80-84 and UsageGuide/README.md:139-195.
+namespace {
+struct SecView { const uint8_t* p = nullptr; size_t n = 0; };
+
+uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+uint64_t rd64(const uint8_t* p) { uint64_t v; memcpy(&v, p, 8); return v; }
+
+void split_container(const uint8_t* b, size_t len, SecView sec[11]) {
+    if (!b || len < 12 || memcmp(b, "zkey", 4) != 0) throw std::runtime_error("not a .zkey file (bad magic)");
+    if (rd32(b + 4) != 1) throw std::runtime_error("unsupported .zkey version");
+    const uint32_t n_sec = rd32(b + 8);
+    size_t pos = 12;
+    for (uint32_t i = 0; i < n_sec; ++i) {
+        if (pos + 12 > len) throw std::runtime_error("truncated .zkey (section header)");
+        const uint32_t type = rd32(b + pos);
+        const uint64_t size = rd64(b + pos + 4);
+        pos += 12;
+        if (size > len - pos) throw std::runtime_error("truncated .zkey (section " + std::to_string(type) + ")");
+        if (type >= 1 && type <= 10) sec[type] = SecView{b + pos, (size_t)size};
+        pos += (size_t)size;
+    }
+}
+
+template <class F> __device__ __forceinline__ bool canonical(const F& x);
+template <> __device__ __forceinline__ bool canonical<dev::Fq>(const dev::Fq& x) { dev::Fq t = x; t.reduce_once(); return t == x; }
+template <> __device__ __forceinline__ bool canonical<dev::Fq2>(const dev::Fq2& x) { return canonical(x.c0) && canonical(x.c1); }
+
+// every point either all-zero (infinity) or on y^2 = x^3 + b with canonical (< q) coordinates
+template <class F>
+__global__ void validate_points_kernel(const uint8_t* __restrict__ pts, uint32_t n, F b, uint32_t* bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const dev::Affine<F> p = dev::Affine<F>::load(pts + sizeof(dev::Affine<F>) * (size_t)i);
+    if (p.is_inf()) return;
+    if (!canonical(p.x) || !canonical(p.y) || !(p.y.sqr() == p.x.sqr() * p.x + b)) atomicMin(bad, i);
+}
+
+template <class F, class HostF>
+void validate_points(const DevBuf& buf, size_t n, const HostF& b_host, const char* what, uint32_t* flag_dev) {
+    if (!n) return;
+    F b;
+    static_assert(sizeof(F) == sizeof(HostF), "host / device field images differ");
+    memcpy(&b, &b_host, sizeof(F));
+    CUDA_OK(cudaMemset(flag_dev, 0xff, 4));
+    validate_points_kernel<F><<<(unsigned)((n + 127) / 128), 128>>>(buf.p, (uint32_t)n, b, flag_dev);
+    ZKE_COUNT_LAUNCH(1);
+    CHECK_LAUNCH();
+    uint32_t bad = 0;
+    CUDA_OK(cudaMemcpy(&bad, flag_dev, 4, cudaMemcpyDeviceToHost));
+    if (bad != 0xffffffffu) throw std::runtime_error(std::string(".zkey section ") + what + ": point " + std::to_string(bad) + " is not on the curve");
+}
+
+Fq2 g2_twist_b() { return Fq2{Fq::from_u64(3), Fq::zero()} * Fq2{Fq::from_u64(9), Fq::one()}.inv(); }
+
+struct U256HashE {
+    size_t operator()(const U256& x) const { return (size_t)(x.v[0] * 0x9E3779B97F4A7C15ull ^ x.v[1] * 31 ^ x.v[2] * 131 ^ x.v[3]); }
+};
+}  // namespace
+
+static zke_zkey* do_zkey_load(const SecView sec[11], int device) {
+    select_device(device);
+    for (int s = 1; s <= 9; ++s) if (!sec[s].p) throw std::runtime_error(".zkey section " + std::to_string(s) + " is missing");
+    if (sec[1].n < 4 || rd32(sec[1].p) != 1) throw std::runtime_error("not a Groth16 .zkey (protocol id)");
+    const uint8_t* h = sec[2].p;
+    const size_t HDR = 4 + 32 + 4 + 32 + 12 + 64 + 64 + 128 + 128 + 64 + 128;
+    if (sec[2].n < HDR) throw std::runtime_error(".zkey header section too short");
+    if (rd32(h) != 32 || memcmp(h + 4, fq_params().p.v, 32) != 0) throw std::runtime_error(".zkey is not over the BN254 base field");
+    if (rd32(h + 36) != 32 || memcmp(h + 40, fr_params().p.v, 32) != 0) throw std::runtime_error(".zkey is not over the BN254 scalar field");
+    std::unique_ptr<zke_zkey> zk(new zke_zkey());
+    zk->device = device;
+    zk->n_vars = rd32(h + 72); zk->n_public = rd32(h + 76);
+    const uint32_t domain = rd32(h + 80);
+    if (domain == 0 || (domain & (domain - 1)) || domain > (1u << 28)) throw std::runtime_error(".zkey domain size is not a power of two <= 2^28");
+    zk->log_n = 0;
+    while ((1u << zk->log_n) < domain) zk->log_n++;
+    const uint32_t m = zk->n_vars, l = zk->n_public;
+    if (m == 0 || l + 1 > m) throw std::runtime_error(".zkey header: nPublic + 1 > nVars");
+    const size_t N = domain;
+    auto need = [&](int s, size_t bytes) {
+        if (sec[s].n != bytes) throw std::runtime_error(".zkey section " + std::to_string(s) + " has " + std::to_string(sec[s].n) + " bytes, expected " + std::to_string(bytes));
+    };
+    need(3, (size_t)(l + 1) * 64); need(5, (size_t)m * 64); need(6, (size_t)m * 64); need(7, (size_t)m * 128);
+    need(8, (size_t)(m - l - 1) * 64); need(9, N * 64);
+
+    // header points and IC: host copies, checked on the host
+    const uint8_t* q = h + 84;
+    memcpy(&zk->alpha1, q, 64); memcpy(&zk->beta1, q + 64, 64); memcpy(&zk->beta2, q + 128, 128);
+    memcpy(&zk->gamma2, q + 256, 128); memcpy(&zk->delta1, q + 384, 64); memcpy(&zk->delta2, q + 448, 128);
+    auto fq_ok = [](const Fq& x) { return u256_cmp(x.m, fq_params().p) < 0; };
+    auto g1_ok = [&](const G1AffineH& p) { return fq_ok(p.x) && fq_ok(p.y) && g1_on_curve(p); };
+    auto g2_ok = [&](const G2AffineH& p) { return fq_ok(p.x.c0) && fq_ok(p.x.c1) && fq_ok(p.y.c0) && fq_ok(p.y.c1) && g2_on_curve(p); };
+    if (!g1_ok(zk->alpha1) || !g1_ok(zk->beta1) || !g1_ok(zk->delta1) || !g2_ok(zk->beta2) || !g2_ok(zk->gamma2) || !g2_ok(zk->delta2))
+        throw std::runtime_error(".zkey header: a key point is not on its curve");
+    zk->ic.resize(l + 1);
+    memcpy(zk->ic.data(), sec[3].p, (size_t)(l + 1) * 64);
+    for (auto& p : zk->ic) if (!g1_ok(p)) throw std::runtime_error(".zkey section 3: an IC point is not on the curve");
+
+    // section 4 -> CSR of A and B over the N domain rows
+    {
+        if (sec[4].n < 4) throw std::runtime_error(".zkey section 4 too short");
+        const uint32_t n_rec = rd32(sec[4].p);
+        if (sec[4].n != 4 + (size_t)n_rec * 44) throw std::runtime_error(".zkey section 4: size does not match its record count");
+        const uint8_t* rec = sec[4].p + 4;
+        zk->a_ptr.assign(N + 1, 0); zk->b_ptr.assign(N + 1, 0);
+        for (uint32_t k = 0; k < n_rec; ++k) {
+            const uint8_t* r = rec + 44 * (size_t)k;
+            const uint32_t mat = rd32(r), row = rd32(r + 4), sig = rd32(r + 8);
+            if (mat > 1 || row >= N || sig >= m) throw std::runtime_error(".zkey section 4: record " + std::to_string(k) + " out of range");
+            (mat == 0 ? zk->a_ptr : zk->b_ptr)[row + 1]++;
+        }
+        for (size_t i = 0; i < N; ++i) { zk->a_ptr[i + 1] += zk->a_ptr[i]; zk->b_ptr[i + 1] += zk->b_ptr[i]; }
+        zk->a_var.resize(zk->a_ptr[N]); zk->a_coef.resize(zk->a_ptr[N]);
+        zk->b_var.resize(zk->b_ptr[N]); zk->b_coef.resize(zk->b_ptr[N]);
+        std::vector<uint32_t> ca(zk->a_ptr.begin(), zk->a_ptr.end() - 1), cb(zk->b_ptr.begin(), zk->b_ptr.end() - 1);
+        // stored value = c R^2 mod r; interned on the stored image, converted once per distinct value
+        const Fr r_elem = Fr::from_u256(fr_params().r);          // the field element R mod r
+        const Fr rinv2 = (r_elem * r_elem).inv();
+        std::unordered_map<U256, uint32_t, U256HashE> index;
+        for (uint32_t k = 0; k < n_rec; ++k) {
+            const uint8_t* r = rec + 44 * (size_t)k;
+            const uint32_t mat = rd32(r), row = rd32(r + 4), sig = rd32(r + 8);
+            U256 raw;
+            memcpy(raw.v, r + 12, 32);
+            auto it = index.find(raw);
+            if (it == index.end()) {
+                if (u256_cmp(raw, fr_params().p) >= 0) throw std::runtime_error(".zkey section 4: coefficient not reduced mod r");
+                it = index.emplace(raw, (uint32_t)zk->coefs.size()).first;
+                zk->coefs.push_back((Fr::from_u256(raw) * rinv2).to_u256());
+            }
+            if (mat == 0) { const uint32_t pos = ca[row]++; zk->a_var[pos] = sig; zk->a_coef[pos] = it->second; }
+            else { const uint32_t pos = cb[row]++; zk->b_var[pos] = sig; zk->b_coef[pos] = it->second; }
+        }
+        if (zk->coefs.size() >= (1u << 24)) throw std::runtime_error(".zkey has more than 2^24 distinct coefficients");
+        zk->has_coefs = true;
+    }
+
+    // point sections: the file image is the device image
+    DevBuf flag, scratch;
+    flag.alloc(4);
+    const Fq b1 = Fq::from_u64(3);
+    const Fq2 b2 = g2_twist_b();
+    auto up = [&](DevBuf& dst, const uint8_t* src, size_t bytes, size_t skip) {
+        dst.alloc(skip + bytes);
+        if (skip) CUDA_OK(cudaMemset(dst.p, 0, skip));
+        if (bytes) CUDA_OK(cudaMemcpy(dst.p + skip, src, bytes, cudaMemcpyHostToDevice));
+    };
+    up(zk->A, sec[5].p, sec[5].n, 0);   validate_points<dev::Fq>(zk->A, m, b1, "5 (A)", (uint32_t*)flag.p);
+    up(zk->B1, sec[6].p, sec[6].n, 0);  validate_points<dev::Fq>(zk->B1, m, b1, "6 (B1)", (uint32_t*)flag.p);
+    up(zk->B2, sec[7].p, sec[7].n, 0);  validate_points<dev::Fq2>(zk->B2, m, b2, "7 (B2)", (uint32_t*)flag.p);
+    up(zk->C, sec[8].p, sec[8].n, (size_t)(l + 1) * 64);   // C / "L": infinity for the public signals
+    validate_points<dev::Fq>(zk->C, m, b1, "8 (C)", (uint32_t*)flag.p);
+    h_table_config(zk.get(), N);
+    zk->H.alloc((size_t)zk->h_levels * N * sizeof(dev::G1Affine));
+    CUDA_OK(cudaMemcpy(zk->H.p, sec[9].p, N * 64, cudaMemcpyHostToDevice));
+    validate_points<dev::Fq>(zk->H, N, b1, "9 (H)", (uint32_t*)flag.p);
+    scratch.alloc((size_t)SETUP_SLAB * sizeof(dev::G1XYZZ));
+    build_h_levels(zk.get(), N, scratch.p, nullptr);
+    return zk.release();
+}
+
+// `.zkey` writer (sections in file order 1..10; the record order of section 4 is A rows, B rows, then the extra rows)
+static int64_t do_zkey_write(const zke_zkey* zk, const zke_circuit* zc, uint8_t* out, size_t cap) {
+    const uint32_t m = zk->n_vars, l = zk->n_public;
+    const size_t N = (size_t)1 << zk->log_n;
+    const Circuit* c = zc ? &zc->c : nullptr;
+    if (!zk->has_coefs) {
+        if (!c) throw std::runtime_error("a key made by zke_setup needs its circuit to write the coefficient section");
+        if (c->n_vars != m || c->n_public() != l || c->domain_log2() != zk->log_n) throw std::runtime_error("zkey does not belong to this circuit");
+    }
+    size_t n_rec;
+    if (zk->has_coefs) n_rec = zk->a_var.size() + zk->b_var.size();
+    else n_rec = c->a_var.size() + c->b_var.size() + l + 1;
+    const size_t HDR = 4 + 32 + 4 + 32 + 12 + 64 + 64 + 128 + 128 + 64 + 128;
+    const size_t sizes[11] = {0, 4, HDR, (size_t)(l + 1) * 64, 4 + n_rec * 44, (size_t)m * 64, (size_t)m * 64, (size_t)m * 128,
+                              (size_t)(m - l - 1) * 64, N * 64, 68};
+    size_t total = 12;
+    for (int s = 1; s <= 10; ++s) total += 12 + sizes[s];
+    if (!out) return (int64_t)total;
+    if (cap < total) return -2;
+    CUDA_OK(cudaSetDevice(zk->device));
+    uint8_t* p = out;
+    auto w32 = [&](uint32_t v) { memcpy(p, &v, 4); p += 4; };
+    auto w64 = [&](uint64_t v) { memcpy(p, &v, 8); p += 8; };
+    auto wraw = [&](const void* src, size_t n) { memcpy(p, src, n); p += n; };
+    auto sec_hdr = [&](int s) { w32((uint32_t)s); w64(sizes[s]); };
+    memcpy(p, "zkey", 4); p += 4; w32(1); w32(10);
+    sec_hdr(1); w32(1);
+    sec_hdr(2);
+    w32(32); wraw(fq_params().p.v, 32); w32(32); wraw(fr_params().p.v, 32); w32(m); w32(l); w32((uint32_t)N);
+    wraw(&zk->alpha1, 64); wraw(&zk->beta1, 64); wraw(&zk->beta2, 128); wraw(&zk->gamma2, 128); wraw(&zk->delta1, 64); wraw(&zk->delta2, 128);
+    sec_hdr(3); wraw(zk->ic.data(), (size_t)(l + 1) * 64);
+    sec_hdr(4); w32((uint32_t)n_rec);
+    {
+        const std::vector<U256>& coefs = zk->has_coefs ? zk->coefs : c->coefs;
+        const Fr r_elem = Fr::from_u256(fr_params().r);
+        const Fr r2 = r_elem * r_elem;
+        std::vector<U256> stored(coefs.size());
+        for (size_t i = 0; i < coefs.size(); ++i) stored[i] = (Fr::from_u256(coefs[i]) * r2).to_u256();
+        auto rows = [&](uint32_t mat, const std::vector<uint32_t>& ptr, const std::vector<uint32_t>& var, const std::vector<uint32_t>& coef, size_t n_rows) {
+            for (size_t row = 0; row < n_rows; ++row)
+                for (uint32_t k = ptr[row]; k < ptr[row + 1]; ++k) { w32(mat); w32((uint32_t)row); w32(var[k]); wraw(stored[coef[k]].v, 32); }
+        };
+        if (zk->has_coefs) {
+            rows(0, zk->a_ptr, zk->a_var, zk->a_coef, N);
+            rows(1, zk->b_ptr, zk->b_var, zk->b_coef, N);
+        } else {
+            rows(0, c->a_ptr, c->a_var, c->a_coef, c->n_constraints);
+            rows(1, c->b_ptr, c->b_var, c->b_coef, c->n_constraints);
+            const U256 one_r2 = r2.to_u256();
+            for (uint32_t j = 0; j <= l; ++j) { w32(0); w32(c->n_constraints + j); w32(j); wraw(one_r2.v, 32); }
+        }
+    }
+    auto dev_sec = [&](int s, const DevBuf& b, size_t skip) {
+        sec_hdr(s);
+        if (sizes[s]) CUDA_OK(cudaMemcpy(p, b.p + skip, sizes[s], cudaMemcpyDeviceToHost));
+        p += sizes[s];
+    };
+    dev_sec(5, zk->A, 0); dev_sec(6, zk->B1, 0); dev_sec(7, zk->B2, 0); dev_sec(8, zk->C, (size_t)(l + 1) * 64); dev_sec(9, zk->H, 0);
+    sec_hdr(10); memset(p, 0, 68); p += 68;    // circuit hash placeholder, zero contributions
+    return (int64_t)(p - out);
+}
+
 // ------------------------------------------------------------------------------------------------ ctx
+static void alloc_slot(zke_ctx* x, zke_ctx::Slot& S) {
+    if (S.allocated) return;
+    S.w_all.alloc(x->stride * 32 * x->max_batch);
+    S.inputs.alloc((size_t)std::max(1u, x->n_inputs) * 32 * x->max_batch);
+    S.first_bad.alloc(4 * (size_t)x->max_batch);
+    if (x->zkey) {
+        S.results.alloc((size_t)x->max_batch * ZKE_RESULT_STRIDE);
+        CUDA_OK(cudaHostAlloc((void**)&S.results_host, (size_t)x->max_batch * ZKE_RESULT_STRIDE, cudaHostAllocDefault));
+        CUDA_OK(cudaHostAlloc((void**)&S.publics_host, (size_t)x->max_batch * std::max(1u, x->n_public) * 32, cudaHostAllocDefault));
+        S.done.resize(x->max_batch);
+        for (auto& e : S.done) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&S.witness_done, cudaEventDisableTiming));
+    }
+    S.allocated = true;
+}
+
 static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, uint32_t max_batch) {
     select_device(device);
-    const Circuit& c = zc->c;
-    if (zk && (zk->n_vars != c.n_vars || zk->n_public != c.n_public() || zk->log_n != c.domain_log2()))
+    const Circuit* cp = zc ? &zc->c : nullptr;
+    if (!cp && !(zk && zk->has_coefs)) throw std::runtime_error("a context needs a circuit, or a proving key loaded from a .zkey");
+    if (zk && cp && (zk->n_vars != cp->n_vars || zk->n_public != cp->n_public() || zk->log_n != cp->domain_log2()))
         throw std::runtime_error("zkey does not belong to this circuit");
     if (zk && zk->device != device) throw std::runtime_error("zkey lives on another device");
     if (max_batch == 0) throw std::runtime_error("max_batch must be positive");
     std::unique_ptr<zke_ctx> x(new zke_ctx());
     x->circuit = zc; x->zkey = zk; x->device = device; x->max_batch = max_batch;
-    CUDA_OK(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
+    x->n_vars = cp ? cp->n_vars : zk->n_vars;
+    x->n_public = cp ? cp->n_public() : zk->n_public;
+    x->n_inputs = cp ? cp->n_inputs() : 0;
+    int prio_least = 0, prio_greatest = 0;
+    CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    CUDA_OK(cudaStreamCreateWithPriority(&x->stream, cudaStreamNonBlocking, prio_greatest));
+
+    // coefficient words (lc_term.cuh) of the circuit's - or the key's - interned coefficient table
+    const std::vector<U256>& coefs = cp ? cp->coefs : zk->coefs;
+    {
+        std::vector<uint32_t>& coef_word = x->coef_word;
+        coef_word.assign(coefs.size(), 0);
+        if (coefs.size() >= (1u << 24)) throw std::runtime_error("too many distinct coefficients");
+        for (size_t i = 0; i < coefs.size(); ++i) {
+            auto log2_exact = [](const U256& v) -> int {   // k if v == 2^k, else -1
+                int k = -1, bits = 0;
+                for (unsigned b = 0; b < 256; ++b) if (u256_bit(v, b)) { k = (int)b; ++bits; }
+                return bits == 1 ? k : -1;
+            };
+            U256 neg;
+            u256_sub(neg, fr_params().p, coefs[i]);
+            const int kp = log2_exact(coefs[i]), kn = log2_exact(neg);
+            uint32_t kind = 4, k = 0;
+            if (kp == 0) kind = 0;
+            else if (kn == 0) kind = 1;
+            else if (kp > 0 && kp <= 252 && i <= 0xffffu) { kind = 2; k = (uint32_t)kp; }
+            else if (kn > 0 && kn <= 252 && i <= 0xffffu) { kind = 3; k = (uint32_t)kn; }
+            coef_word[i] = kind == 4 ? ((uint32_t)i | (4u << 24)) : (((uint32_t)i & 0xffffu) | (k << 16) | (kind << 24));
+        }
+        // coefficient table scaled by R: as Montgomery numbers these are just the Montgomery forms
+        std::vector<Fr> cr(std::max<size_t>(1, coefs.size()));
+        for (size_t i = 0; i < coefs.size(); ++i) cr[i] = Fr::from_u256(coefs[i]);
+        x->coef_r.upload(cr);
+    }
 
     // witness program
-    {
+    if (cp) {
+        const Circuit& c = *cp;
         // Streamed witness program (device_engine.cuh): per level, ops sorted by kind / size so that the threads of an
         // iteration do similar work, padded with no-ops to whole iterations of WITNESS_THREADS records; the LC terms
         // of an iteration form one contiguous, 16-byte aligned block.
@@ -269,26 +590,7 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         packed.reserve(4 * (c.ops.size() + (size_t)T * c.n_levels()));
         terms.reserve(2 * c.lc_var.size() + 16);
         auto lc_len = [&](uint32_t id) { return c.lc_ptr[id + 1] - c.lc_ptr[id]; };
-        // term word: coefficient index | k << 16 | kind << 24 (witness.cu: term_value)
-        if (c.coefs.size() > 0xffffu) throw std::runtime_error("too many distinct coefficients for the streamed witness program");
-        std::vector<uint32_t>& coef_word = x->coef_word;
-        coef_word.assign(c.coefs.size(), 0);
-        for (size_t i = 0; i < c.coefs.size(); ++i) {
-            auto log2_exact = [](const U256& v) -> int {   // k if v == 2^k, else -1
-                int k = -1, bits = 0;
-                for (unsigned b = 0; b < 256; ++b) if (u256_bit(v, b)) { k = (int)b; ++bits; }
-                return bits == 1 ? k : -1;
-            };
-            U256 neg;
-            u256_sub(neg, fr_params().p, c.coefs[i]);
-            const int kp = log2_exact(c.coefs[i]), kn = log2_exact(neg);
-            uint32_t kind = 4, k = 0;
-            if (kp == 0) kind = 0;
-            else if (kn == 0) kind = 1;
-            else if (kp > 0 && kp <= 252) { kind = 2; k = (uint32_t)kp; }
-            else if (kn > 0 && kn <= 252) { kind = 3; k = (uint32_t)kn; }
-            coef_word[i] = (uint32_t)i | (k << 16) | (kind << 24);
-        }
+        const std::vector<uint32_t>& coef_word = x->coef_word;
         std::vector<uint32_t> order;
         std::vector<uint64_t> keys;
         for (uint32_t lvl = 0; lvl < c.n_levels(); ++lvl) {
@@ -370,10 +672,6 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         std::vector<uint32_t> aux = c.aux;
         if (aux.empty()) aux.push_back(0);
         x->aux.upload(aux);
-        // coefficient table scaled by R: as Montgomery numbers these are just the Montgomery forms
-        std::vector<Fr> cr(c.coefs.size());
-        for (size_t i = 0; i < cr.size(); ++i) cr[i] = Fr::from_u256(c.coefs[i]);
-        x->coef_r.upload(cr);
         const uint32_t NSMALL = 4096;
         std::vector<Fr> inv(NSMALL);
         for (uint32_t i = 0; i < NSMALL; ++i) inv[i] = Fr::from_u64(i);
@@ -389,25 +687,35 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         P.n_iters = n_iters; P.n_ops = (uint32_t)c.ops.size(); P.n_vars = c.n_vars; P.n_temps = c.n_temps;
         P.n_outputs = c.n_outputs; P.n_inputs = c.n_inputs();
     }
-    // R1CS
+    // R1CS (the circuit's A, B, C) or the QAP matrices of the key (A, B incl. the extra public rows; no C)
     {
         auto up_terms = [&](const std::vector<uint32_t>& var, const std::vector<uint32_t>& coef, DevBuf& dst) {
             std::vector<uint32_t> t(2 * var.size() + 2);
             for (size_t i = 0; i < var.size(); ++i) { t[2 * i] = var[i]; t[2 * i + 1] = x->coef_word[coef[i]]; }
             dst.upload(t);
         };
-        x->a_ptr.upload(c.a_ptr); x->b_ptr.upload(c.b_ptr); x->c_ptr.upload(c.c_ptr);
-        up_terms(c.a_var, c.a_coef, x->a_terms); up_terms(c.b_var, c.b_coef, x->b_terms); up_terms(c.c_var, c.c_coef, x->c_terms);
         dev::DevR1cs& R = x->r1cs;
-        R.a_ptr = (const uint32_t*)x->a_ptr.p; R.b_ptr = (const uint32_t*)x->b_ptr.p; R.c_ptr = (const uint32_t*)x->c_ptr.p;
-        R.a_terms = (const uint2*)x->a_terms.p; R.b_terms = (const uint2*)x->b_terms.p; R.c_terms = (const uint2*)x->c_terms.p;
-        R.coef_r = x->coef_r.p; R.n_constraints = c.n_constraints; R.n_public = c.n_public(); R.n_vars = c.n_vars;
+        if (cp) {
+            const Circuit& c = *cp;
+            x->a_ptr.upload(c.a_ptr); x->b_ptr.upload(c.b_ptr); x->c_ptr.upload(c.c_ptr);
+            up_terms(c.a_var, c.a_coef, x->a_terms); up_terms(c.b_var, c.b_coef, x->b_terms); up_terms(c.c_var, c.c_coef, x->c_terms);
+            R.c_ptr = (const uint32_t*)x->c_ptr.p; R.c_terms = (const uint2*)x->c_terms.p;
+            R.n_constraints = c.n_constraints; R.n_public = c.n_public();
+        } else {
+            x->a_ptr.upload(zk->a_ptr); x->b_ptr.upload(zk->b_ptr);
+            up_terms(zk->a_var, zk->a_coef, x->a_terms); up_terms(zk->b_var, zk->b_coef, x->b_terms);
+            R.c_ptr = nullptr; R.c_terms = nullptr;
+            R.n_constraints = 1u << zk->log_n; R.n_public = 0;    // every domain row comes from the key's matrices
+        }
+        R.a_ptr = (const uint32_t*)x->a_ptr.p; R.b_ptr = (const uint32_t*)x->b_ptr.p;
+        R.a_terms = (const uint2*)x->a_terms.p; R.b_terms = (const uint2*)x->b_terms.p;
+        R.coef_r = x->coef_r.p; R.n_vars = x->n_vars;
     }
-    x->stride = (size_t)c.n_vars + c.n_temps;
-    x->w_all.alloc(x->stride * 32 * max_batch);
-    x->inputs.alloc((size_t)std::max(1u, c.n_inputs()) * 32 * max_batch);
-    x->first_bad.alloc(4 * (size_t)max_batch);
+    x->stride = (size_t)x->n_vars + (cp ? cp->n_temps : 0);
+    x->inputs.alloc((size_t)std::max(1u, x->n_inputs) * 32 * max_batch);
+    x->check_flag.alloc(8);
     x->bad_host.resize(max_batch);
+    alloc_slot(x.get(), x->slots[0]);
 
     if (zk) {
         const unsigned log_n = zk->log_n;
@@ -446,49 +754,53 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         x->ntt.tw_fwd = x->tw_fwd.p; x->ntt.tw_inv = x->tw_inv.p; x->ntt.log_n = (int)log_n;
         x->cfg_w = dev::msm_config_witness();
         x->cfg_h = zk->cfg_h;
-        size_t ws = std::max(dev::MsmPlan<dev::Fq>::workspace_bytes(c.n_vars, x->cfg_w),
+        size_t ws = std::max(dev::MsmPlan<dev::Fq>::workspace_bytes(x->n_vars, x->cfg_w),
                              dev::MsmPlan<dev::Fq>::workspace_bytes((uint32_t)N, x->cfg_h));
-        ws = std::max(ws, dev::MsmPlan<dev::Fq2>::workspace_bytes(c.n_vars, x->cfg_w));
+        ws = std::max(ws, dev::MsmPlan<dev::Fq2>::workspace_bytes(x->n_vars, x->cfg_w));
         int want = 8;
         if (const char* e = getenv("ZKE_LANES")) want = atoi(e);
         if (const char* e = getenv("ZKE_SPLIT_STREAMS")) x->split_streams = atoi(e) != 0;
+        if (const char* e = getenv("ZKE_FINISH_THREADS")) x->finish_threads = std::max(1, std::min(32, atoi(e)));
         want = std::max(1, std::min(ZKE_MAX_LANES, std::min<int>(want, (int)max_batch)));
+        // the lanes' light streams sit one priority step below the witness stream (when the device offers three levels)
+        const int prio_light = prio_greatest < prio_least - 1 ? prio_greatest + 1 : prio_greatest;
         for (int i = 0; i < want; ++i) {
             zke_ctx::Lane& L = x->lanes[i];
-            int prio_least = 0, prio_greatest = 0;
-            CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
-            CUDA_OK(cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, prio_greatest));
+            CUDA_OK(cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, prio_light));
             CUDA_OK(cudaStreamCreateWithPriority(&L.heavy, cudaStreamNonBlocking, prio_least));
             for (auto& e : L.ev) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             L.va.alloc(N * 32); L.vb.alloc(N * 32); L.vc.alloc(N * 32); L.vd.alloc(N * 32);
             L.msm_ws.alloc(ws);
         }
         x->lanes_alloc = x->n_lanes = want;
-        x->results.alloc((size_t)max_batch * ZKE_RESULT_STRIDE);
-        CUDA_OK(cudaHostAlloc((void**)&x->results_host, (size_t)max_batch * ZKE_RESULT_STRIDE, cudaHostAllocDefault));
-        CUDA_OK(cudaHostAlloc((void**)&x->publics_host, (size_t)max_batch * std::max(1u, c.n_public()) * 32, cudaHostAllocDefault));
-        x->done.resize(max_batch);
-        for (auto& e : x->done) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        CUDA_OK(cudaEventCreateWithFlags(&x->witness_done, cudaEventDisableTiming));
     }
     CUDA_OK(cudaDeviceSynchronize());
     return x.release();
 }
 
 static std::string assert_message(const zke_ctx* x, uint32_t email, uint32_t row) {
-    const Circuit& c = x->circuit->c;
-    std::string scope = row < c.scope_of_constraint.size() ? c.scopes[c.scope_of_constraint[row]] : "?";
+    std::string scope = "?";
+    if (x->circuit) {
+        const Circuit& c = x->circuit->c;
+        if (row < c.scope_of_constraint.size()) scope = c.scopes[c.scope_of_constraint[row]];
+    }
     return "Assert Failed: constraint " + std::to_string(row) + " in template " + scope + " @ email " + std::to_string(email);
 }
 
-// Runs the witness kernel for `batch` emails whose inputs are in host memory.
-static void do_witness(zke_ctx* x, const uint8_t* inputs, size_t batch) {
+static void require_idle(const zke_ctx* x) {
+    if (x->n_submitted != x->n_collected) throw std::runtime_error("a submitted batch is still in flight: call zke_fullprove_collect first");
+}
+
+// Runs the witness kernel of `batch` emails into slot S.  inputs: host memory, or NULL for the resident inputs.
+static void do_witness(zke_ctx* x, zke_ctx::Slot& S, const uint8_t* inputs, size_t batch) {
+    if (!x->circuit) throw std::runtime_error("this context was opened from a .zkey alone: it has no witness program (use zke_load_witness / zke_wtns_prove)");
     const Circuit& c = x->circuit->c;
     if (batch == 0 || batch > x->max_batch) throw std::runtime_error("batch exceeds the context's max_batch");
     CUDA_OK(cudaSetDevice(x->device));
+    const uint8_t* in_dev = x->inputs.p;
     if (inputs) {
-        if (c.n_inputs()) CUDA_OK(cudaMemcpyAsync(x->inputs.p, inputs, (size_t)c.n_inputs() * 32 * batch, cudaMemcpyHostToDevice, x->stream));
-        x->inputs_resident = (uint32_t)batch;
+        if (c.n_inputs()) CUDA_OK(cudaMemcpyAsync(S.inputs.p, inputs, (size_t)c.n_inputs() * 32 * batch, cudaMemcpyHostToDevice, x->stream));
+        in_dev = S.inputs.p;
     } else if (x->inputs_resident < batch) {
         throw std::runtime_error("inputs == NULL but no (or too few) inputs are resident: call zke_upload_inputs first");
     }
@@ -499,7 +811,7 @@ static void do_witness(zke_ctx* x, const uint8_t* inputs, size_t batch) {
         tr.alloc(8 * ((size_t)x->prog.n_iters + 1));
         dev::DevProgram P = x->prog;
         P.trace = (unsigned long long*)tr.p;
-        dev::launch_witness(P, x->w_all.p, x->stride, x->inputs.p, (uint32_t)batch, x->stream);
+        dev::launch_witness(P, S.w_all.p, x->stride, in_dev, (uint32_t)batch, x->stream);
         CUDA_OK(cudaStreamSynchronize(x->stream));
         std::vector<unsigned long long> h(x->prog.n_iters);
         CUDA_OK(cudaMemcpy(h.data(), tr.p, 8 * h.size(), cudaMemcpyDeviceToHost));
@@ -509,24 +821,26 @@ static void do_witness(zke_ctx* x, const uint8_t* inputs, size_t batch) {
             fclose(f);
         }
     }
-    dev::launch_witness(x->prog, x->w_all.p, x->stride, x->inputs.p, (uint32_t)batch, x->stream);
+    dev::launch_witness(x->prog, S.w_all.p, x->stride, in_dev, (uint32_t)batch, x->stream);
+    CHECK_LAUNCH();
     if (x->profile) x->spans.push_back({ZKE_STAGE_WITNESS, p0, x->mark()});
-    x->loaded = (uint32_t)batch;
+    S.loaded = (uint32_t)batch;
 }
 
 // constraint check only (no zkey needed): uses scratch a/b vectors sized to n_constraints
-static int do_check(zke_ctx* x, size_t batch, int32_t* status, std::string& msg) {
+static int do_check(zke_ctx* x, zke_ctx::Slot& S, size_t batch, int32_t* status, std::string& msg) {
     const Circuit& c = x->circuit->c;
     const uint32_t rows = c.n_constraints + c.n_public() + 1;
     DevBuf ta, tb;
     uint8_t *pa, *pb;
     if (x->lanes[0].va.p && x->lanes[0].va.bytes >= (size_t)rows * 32) { pa = x->lanes[0].va.p; pb = x->lanes[0].vb.p; }
     else { ta.alloc((size_t)rows * 32); tb.alloc((size_t)rows * 32); pa = ta.p; pb = tb.p; }
-    CUDA_OK(cudaMemsetAsync(x->first_bad.p, 0xff, 4 * batch, x->stream));
+    CUDA_OK(cudaMemsetAsync(S.first_bad.p, 0xff, 4 * batch, x->stream));
     for (size_t e = 0; e < batch; ++e) {
-        dev::launch_build_ab(x->r1cs, x->w_all.p + 32 * x->stride * e, pa, pb, nullptr, rows, (uint32_t*)x->first_bad.p + e, x->stream);
+        dev::launch_build_ab(x->r1cs, S.w_all.p + 32 * x->stride * e, pa, pb, nullptr, rows, (uint32_t*)S.first_bad.p + e, x->stream);
     }
-    CUDA_OK(cudaMemcpyAsync(x->bad_host.data(), x->first_bad.p, 4 * batch, cudaMemcpyDeviceToHost, x->stream));
+    CHECK_LAUNCH();
+    CUDA_OK(cudaMemcpyAsync(x->bad_host.data(), S.first_bad.p, 4 * batch, cudaMemcpyDeviceToHost, x->stream));
     CUDA_OK(cudaStreamSynchronize(x->stream));
     if (x->profile) x->collect();
     int bad = 0;
@@ -554,25 +868,40 @@ static AffineH<F> finish_msm(const uint8_t* block, const dev::MsmConfig& cfg) {
     return acc.to_affine();
 }
 
-static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs_out, uint8_t* publics_out, int32_t* status, std::string& msg) {
-    const Circuit& c = x->circuit->c;
+static void sync_lanes(zke_ctx* x) {
+    cudaStreamSynchronize(x->stream);
+    for (int i = 0; i < x->lanes_alloc; ++i) { cudaStreamSynchronize(x->lanes[i].st); cudaStreamSynchronize(x->lanes[i].heavy); }
+}
+
+// Enqueues every proving kernel of the `batch` witnesses resident in slot S (no host synchronisation).
+static void enqueue_prove(zke_ctx* x, zke_ctx::Slot& S, size_t batch, const uint8_t* rs) {
     const zke_zkey* zk = x->zkey;
     if (!zk) throw std::runtime_error("context was opened without a proving key");
-    if (batch == 0 || batch > x->loaded) throw std::runtime_error("no witness loaded for this batch (call zke_witness first)");
+    if (batch == 0 || batch > S.loaded) throw std::runtime_error("no witness loaded for this batch (call zke_witness first)");
+    if (rs) {   // validated before any GPU work is queued
+        for (size_t e = 0; e < 2 * batch; ++e) {
+            U256 v;
+            memcpy(v.v, rs + 32 * e, 32);
+            if (u256_cmp(v, fr_params().p) >= 0) throw std::runtime_error("r / s not reduced mod the group order");
+        }
+        S.rs.assign(rs, rs + 64 * batch);
+    } else {
+        S.rs.clear();
+    }
     CUDA_OK(cudaSetDevice(x->device));
-    const uint32_t N = 1u << zk->log_n, m = c.n_vars, l = c.n_public();
+    const uint32_t N = 1u << zk->log_n, m = x->n_vars, l = x->n_public;
     const bool prof = x->profile;
     const int n_lanes = prof ? 1 : x->n_lanes;     // stage timing is only meaningful without overlap
     if (const char* e = getenv("ZKE_SPLIT_STREAMS")) x->split_streams = atoi(e) != 0;
     // the witnesses were produced on the main stream; the lanes start after it (and after the public signals copy)
-    if (l) CUDA_OK(cudaMemcpy2DAsync(x->publics_host, (size_t)l * 32, x->w_all.p + 32, x->stride * 32, (size_t)l * 32, batch, cudaMemcpyDeviceToHost, x->stream));
-    CUDA_OK(cudaEventRecord(x->witness_done, x->stream));
-    for (int i = 0; i < n_lanes; ++i) CUDA_OK(cudaStreamWaitEvent(x->lanes[i].st, x->witness_done, 0));
+    if (l) CUDA_OK(cudaMemcpy2DAsync(S.publics_host, (size_t)l * 32, S.w_all.p + 32, x->stride * 32, (size_t)l * 32, batch, cudaMemcpyDeviceToHost, x->stream));
+    CUDA_OK(cudaEventRecord(S.witness_done, x->stream));
+    for (int i = 0; i < n_lanes; ++i) CUDA_OK(cudaStreamWaitEvent(x->lanes[i].st, S.witness_done, 0));
     for (size_t e = 0; e < batch; ++e) {
         zke_ctx::Lane& L = x->lanes[e % n_lanes];
         cudaStream_t st = L.st;
-        const uint8_t* w = x->w_all.p + 32 * x->stride * e;
-        uint8_t* res = x->results.p + (size_t)ZKE_RESULT_STRIDE * e;
+        const uint8_t* w = S.w_all.p + 32 * x->stride * e;
+        uint8_t* res = S.results.p + (size_t)ZKE_RESULT_STRIDE * e;
         uint32_t* flag = (uint32_t*)(res + ZKE_RES_FLAG_OFF);
         size_t t0 = 0, t1 = 0;
         CUDA_OK(cudaMemsetAsync(flag, 0xff, 4, st));
@@ -589,6 +918,7 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
         dev::launch_ntt_dit(L.vb.p, x->ntt, hv);
         dev::launch_ntt_dit(L.vc.p, x->ntt, hv);
         dev::launch_quotient(L.va.p, L.vb.p, L.vc.p, L.vd.p, N, hv);
+        CHECK_LAUNCH();
         if (hv != st) CUDA_OK(cudaEventRecord(L.ev[1], hv));
         if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_NTT, t0, t1}); t0 = t1; }
         // the witness MSMs do not depend on the transforms: with split streams they run on `st` while the lane's NTT
@@ -601,6 +931,7 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
         dev::MsmPlan<dev::Fq>::run(zk->C.p, w, m, x->cfg_w, ws_w, res + 2 * ZKE_RES_G1_BLOCK, st);
         if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MSM_C, t0, t1}); t0 = t1; }
         dev::MsmPlan<dev::Fq2>::run(zk->B2.p, w, m, x->cfg_w, ws_w, res + 4 * ZKE_RES_G1_BLOCK, st);
+        CHECK_LAUNCH();
         if (prof) { t1 = x->mark(st); x->spans.push_back({ZKE_STAGE_MSM_B2, t0, t1}); t0 = t1; }
         if (hv != st) CUDA_OK(cudaStreamWaitEvent(st, L.ev[1], 0));
         {
@@ -616,34 +947,39 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
                 dev::MsmPlan<dev::Fq>::run(zk->H.p, L.vd.p, N, x->cfg_h, L.msm_ws.p, res + 3 * ZKE_RES_G1_BLOCK, st, nullptr, &heavy);
             }
         }
-        CUDA_OK(cudaMemcpyAsync(x->results_host + (size_t)ZKE_RESULT_STRIDE * e, res, ZKE_RESULT_STRIDE, cudaMemcpyDeviceToHost, st));
-        CUDA_OK(cudaEventRecord(x->done[e], st));
+        CHECK_LAUNCH();
+        CUDA_OK(cudaMemcpyAsync(S.results_host + (size_t)ZKE_RESULT_STRIDE * e, res, ZKE_RESULT_STRIDE, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaEventRecord(S.done[e], st));
         // the lane's next email reuses va..vd on `hv`; its first kernels run on `st` (after this point) and `hv`
         // only starts after an event recorded on `st`, so the order is already enforced
     }
+    S.batch = (uint32_t)batch;
+}
 
-    // host tail, overlapped with the GPU work of the later emails
-    int bad = 0;
+// Host tail of a batch enqueued by enqueue_prove: waits per email, finishes the MSMs, assembles pi_A, pi_B, pi_C.
+// `finish_threads` host threads share the emails (3 ms of big-integer work each), overlapped with the GPU work of the
+// later emails and of the next submitted batch.
+static int finish_prove(zke_ctx* x, zke_ctx::Slot& S, uint8_t* proofs_out, uint8_t* publics_out, int32_t* status, std::string& msg) {
+    const zke_zkey* zk = x->zkey;
+    const size_t batch = S.batch;
+    const uint32_t l = x->n_public;
     const G1JacH alpha1 = G1JacH::from_affine(zk->alpha1), beta1 = G1JacH::from_affine(zk->beta1), delta1 = G1JacH::from_affine(zk->delta1);
     const G2JacH beta2 = G2JacH::from_affine(zk->beta2), delta2 = G2JacH::from_affine(zk->delta2);
-    for (size_t e = 0; e < batch; ++e) {
-        CUDA_OK(cudaEventSynchronize(x->done[e]));
-        const uint8_t* res = x->results_host + (size_t)ZKE_RESULT_STRIDE * e;
+    std::vector<int32_t> st_local(batch, -1);
+    std::string first_error;
+    std::mutex err_mutex;
+    auto one = [&](size_t e) {
+        CUDA_OK(cudaEventSynchronize(S.done[e]));
+        const uint8_t* res = S.results_host + (size_t)ZKE_RESULT_STRIDE * e;
         uint32_t flag;
         memcpy(&flag, res + ZKE_RES_FLAG_OFF, 4);
-        int32_t s = flag == 0xffffffffu ? -1 : (int32_t)flag;
-        if (status) status[e] = s;
+        const int32_t s = flag == 0xffffffffu ? -1 : (int32_t)flag;
+        st_local[e] = s;
         uint8_t* out = proofs_out + 256 * e;
-        if (s >= 0) {
-            if (!bad) msg = assert_message(x, (uint32_t)e, (uint32_t)s);
-            ++bad;
-            memset(out, 0, 256);
-            continue;
-        }
+        if (s >= 0) { memset(out, 0, 256); return; }
         U256 r, sc;
-        if (rs) { memcpy(r.v, rs + 64 * e, 32); memcpy(sc.v, rs + 64 * e + 32, 32); }
+        if (!S.rs.empty()) { memcpy(r.v, S.rs.data() + 64 * e, 32); memcpy(sc.v, S.rs.data() + 64 * e + 32, 32); }
         else { random_scalar(r); random_scalar(sc); }
-        if (u256_cmp(r, fr_params().p) >= 0 || u256_cmp(sc, fr_params().p) >= 0) throw std::runtime_error("r / s not reduced mod the group order");
         G1AffineH ma = finish_msm<Fq>(res + 0 * ZKE_RES_G1_BLOCK, x->cfg_w);
         G1AffineH mb1 = finish_msm<Fq>(res + 1 * ZKE_RES_G1_BLOCK, x->cfg_w);
         G1AffineH mc = finish_msm<Fq>(res + 2 * ZKE_RES_G1_BLOCK, x->cfg_w);
@@ -660,13 +996,92 @@ static int do_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs
         write_fq(out + 0, A.x); write_fq(out + 32, A.y);
         write_fq(out + 64, B.x.c0); write_fq(out + 96, B.x.c1); write_fq(out + 128, B.y.c0); write_fq(out + 160, B.y.c1);
         write_fq(out + 192, C.x); write_fq(out + 224, C.y);
+    };
+    const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)x->finish_threads, batch));
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+        try {
+            cudaSetDevice(x->device);
+            for (;;) {
+                const size_t e = next.fetch_add(1);
+                if (e >= batch) break;
+                one(e);
+            }
+        } catch (const std::exception& ex) {
+            std::lock_guard<std::mutex> lock(err_mutex);
+            if (first_error.empty()) first_error = ex.what();
+        }
+    };
+    if (T == 1) worker();
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t) th.emplace_back(worker);
+        for (auto& t : th) t.join();
     }
-    CUDA_OK(cudaStreamSynchronize(x->stream));
-    for (int i = 0; i < n_lanes; ++i) { CUDA_OK(cudaStreamSynchronize(x->lanes[i].st)); CUDA_OK(cudaStreamSynchronize(x->lanes[i].heavy)); }
-    // later work on the main stream (next witness batch) must not overtake the lanes: they are idle now
-    if (prof) x->collect();
-    if (publics_out && l) memcpy(publics_out, x->publics_host, (size_t)l * 32 * batch);
+    // everything of this batch has completed (each email's `done` event closes its lane work; the publics copy
+    // precedes the lanes on the witness stream)
+    if (x->profile) { sync_lanes(x); x->collect(); }
+    if (!first_error.empty()) { sync_lanes(x); throw std::runtime_error(first_error); }
+    int bad = 0;
+    for (size_t e = 0; e < batch; ++e) {
+        if (status) status[e] = st_local[e];
+        if (st_local[e] >= 0) { if (!bad) msg = assert_message(x, (uint32_t)e, (uint32_t)st_local[e]); ++bad; }
+    }
+    if (publics_out && l) memcpy(publics_out, S.publics_host, (size_t)l * 32 * batch);
     return bad;
+}
+
+static int do_prove(zke_ctx* x, zke_ctx::Slot& S, size_t batch, const uint8_t* rs, uint8_t* proofs_out, uint8_t* publics_out, int32_t* status, std::string& msg) {
+    try {
+        enqueue_prove(x, S, batch, rs);
+    } catch (...) {
+        sync_lanes(x);      // nothing of a half-queued batch may keep writing into the result buffers
+        throw;
+    }
+    return finish_prove(x, S, proofs_out, publics_out, status, msg);
+}
+
+// iden3 `.wtns` v2: section 1 {u32 n8, q[n8], u32 nWitness}, section 2 nWitness x n8 bytes (standard form)
+static const uint8_t* parse_wtns(const uint8_t* b, size_t len, uint32_t expect_vars) {
+    if (!b || len < 12 || memcmp(b, "wtns", 4) != 0) throw std::runtime_error("not a .wtns file (bad magic)");
+    const uint32_t n_sec = rd32(b + 8);
+    size_t pos = 12;
+    const uint8_t *s1 = nullptr, *s2 = nullptr;
+    size_t n1 = 0, n2 = 0;
+    for (uint32_t i = 0; i < n_sec; ++i) {
+        if (pos + 12 > len) throw std::runtime_error("truncated .wtns");
+        const uint32_t type = rd32(b + pos);
+        const uint64_t size = rd64(b + pos + 4);
+        pos += 12;
+        if (size > len - pos) throw std::runtime_error("truncated .wtns");
+        if (type == 1) { s1 = b + pos; n1 = (size_t)size; }
+        if (type == 2) { s2 = b + pos; n2 = (size_t)size; }
+        pos += (size_t)size;
+    }
+    if (!s1 || !s2 || n1 < 40) throw std::runtime_error(".wtns sections missing");
+    if (rd32(s1) != 32 || memcmp(s1 + 4, fr_params().p.v, 32) != 0) throw std::runtime_error(".wtns is not over the BN254 scalar field");
+    const uint32_t n = rd32(s1 + 36);
+    if (n != expect_vars) throw std::runtime_error(".wtns has " + std::to_string(n) + " values, the key expects " + std::to_string(expect_vars));
+    if (n2 != (size_t)n * 32) throw std::runtime_error(".wtns data section has the wrong size");
+    return s2;
+}
+
+static void load_witness(zke_ctx* x, zke_ctx::Slot& S, const uint8_t* wtns, size_t batch) {
+    if (batch == 0 || batch > x->max_batch) throw std::runtime_error("batch exceeds the context's max_batch");
+    CUDA_OK(cudaSetDevice(x->device));
+    const size_t m = x->n_vars;
+    CUDA_OK(cudaMemcpy2DAsync(S.w_all.p, x->stride * 32, wtns, m * 32, m * 32, batch, cudaMemcpyHostToDevice, x->stream));
+    // externally computed witnesses are validated: every value canonical (< r) and w[0] == 1
+    CUDA_OK(cudaMemsetAsync(x->check_flag.p, 0, 8, x->stream));
+    dev::launch_check_witness(S.w_all.p, x->stride, (uint32_t)m, (uint32_t)batch, (uint32_t*)x->check_flag.p, x->stream);
+    CHECK_LAUNCH();
+    uint32_t flags[2] = {0, 0};
+    CUDA_OK(cudaMemcpyAsync(flags, x->check_flag.p, 8, cudaMemcpyDeviceToHost, x->stream));
+    CUDA_OK(cudaStreamSynchronize(x->stream));
+    S.loaded = 0;
+    if (flags[0]) throw std::runtime_error("witness value not reduced mod r");
+    if (flags[1]) throw std::runtime_error("witness[0] must be 1");
+    S.loaded = (uint32_t)batch;
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI
@@ -682,6 +1097,26 @@ zke_zkey* zke_setup(const zke_circuit* c, uint64_t seed, int device, char* err, 
     try { if (!c) throw std::runtime_error("null circuit"); return do_setup(c, seed, device); }
     catch (const std::exception& e) { set_err(err, errcap, e.what()); return nullptr; }
 }
+zke_zkey* zke_zkey_load(const void* zkey_bytes, size_t len, int device, char* err, size_t errcap) {
+    try {
+        SecView sec[11];
+        split_container((const uint8_t*)zkey_bytes, len, sec);
+        return do_zkey_load(sec, device);
+    } catch (const std::exception& e) { set_err(err, errcap, e.what()); return nullptr; }
+}
+zke_zkey* zke_zkey_load_chunks(const void* const* chunks, const size_t* lens, size_t n_chunks, int device, char* err, size_t errcap) {
+    try {
+        if (!chunks || !lens || n_chunks < 9) throw std::runtime_error("expected the chunk files b..j (sections 1-9; k is optional)");
+        SecView sec[11];
+        for (size_t i = 0; i < n_chunks && i < 10; ++i) sec[i + 1] = SecView{(const uint8_t*)chunks[i], lens[i]};
+        return do_zkey_load(sec, device);
+    } catch (const std::exception& e) { set_err(err, errcap, e.what()); return nullptr; }
+}
+int64_t zke_zkey_write(const zke_zkey* z, const zke_circuit* c, uint8_t* out, size_t cap) {
+    try { if (!z) return -1; return do_zkey_write(z, c, out, cap); }
+    catch (const std::exception&) { return -3; }
+}
+int zke_zkey_is_toy(const zke_zkey* z) { return z ? (z->toy ? 1 : 0) : -1; }
 void zke_zkey_free(zke_zkey* z) { if (z) { cudaSetDevice(z->device); delete z; } }
 
 int zke_zkey_info(const zke_zkey* z, uint32_t* n_vars, uint32_t* n_public, uint32_t* domain_log2) {
@@ -744,22 +1179,25 @@ int64_t zke_zkey_section(const zke_zkey* z, int section, uint8_t* out, size_t ca
 }
 
 zke_ctx* zke_ctx_open(const zke_circuit* c, const zke_zkey* zkey, int device, uint32_t max_batch, char* err, size_t errcap) {
-    try { if (!c) throw std::runtime_error("null circuit"); return do_open(c, zkey, device, max_batch); }
+    try { return do_open(c, zkey, device, max_batch); }
     catch (const std::exception& e) { set_err(err, errcap, e.what()); return nullptr; }
 }
 void zke_ctx_close(zke_ctx* x) {
     if (!x) return;
     cudaSetDevice(x->device);
+    sync_lanes(x);
     for (auto e : x->ev_pool) cudaEventDestroy(e);
-    for (auto e : x->done) cudaEventDestroy(e);
-    if (x->witness_done) cudaEventDestroy(x->witness_done);
+    for (auto& S : x->slots) {
+        for (auto e : S.done) cudaEventDestroy(e);
+        if (S.witness_done) cudaEventDestroy(S.witness_done);
+        if (S.results_host) cudaFreeHost(S.results_host);
+        if (S.publics_host) cudaFreeHost(S.publics_host);
+    }
     for (int i = 0; i < x->lanes_alloc; ++i) {
         if (x->lanes[i].st) cudaStreamDestroy(x->lanes[i].st);
         if (x->lanes[i].heavy) cudaStreamDestroy(x->lanes[i].heavy);
         for (auto e : x->lanes[i].ev) if (e) cudaEventDestroy(e);
     }
-    if (x->results_host) cudaFreeHost(x->results_host);
-    if (x->publics_host) cudaFreeHost(x->publics_host);
     if (x->stream) cudaStreamDestroy(x->stream);
     delete x;
 }
@@ -768,8 +1206,9 @@ int zke_upload_inputs(zke_ctx* x, const uint8_t* inputs, size_t batch, char* err
     try {
         if (!x || !inputs) throw std::runtime_error("null argument");
         if (batch == 0 || batch > x->max_batch) throw std::runtime_error("batch exceeds the context's max_batch");
+        require_idle(x);
         CUDA_OK(cudaSetDevice(x->device));
-        const size_t n = x->circuit->c.n_inputs();
+        const size_t n = x->n_inputs;
         if (n) CUDA_OK(cudaMemcpy(x->inputs.p, inputs, n * 32 * batch, cudaMemcpyHostToDevice));
         x->inputs_resident = (uint32_t)batch;
         return 0;
@@ -798,12 +1237,14 @@ uint64_t zke_kernel_launches(void) { return dev::g_kernel_launches; }
 int zke_witness(zke_ctx* x, const uint8_t* inputs, size_t batch, uint8_t* wtns_out, int32_t* status, char* err, size_t errcap) {
     try {
         if (!x) throw std::runtime_error("null context");
-        do_witness(x, inputs, batch);
+        require_idle(x);
+        zke_ctx::Slot& S = x->slots[0];
+        do_witness(x, S, inputs, batch);
         std::string msg;
-        int bad = do_check(x, batch, status, msg);
+        int bad = do_check(x, S, batch, status, msg);
         if (wtns_out) {
-            const size_t m = x->circuit->c.n_vars;
-            CUDA_OK(cudaMemcpy2D(wtns_out, m * 32, x->w_all.p, x->stride * 32, m * 32, batch, cudaMemcpyDeviceToHost));
+            const size_t m = x->n_vars;
+            CUDA_OK(cudaMemcpy2D(wtns_out, m * 32, S.w_all.p, x->stride * 32, m * 32, batch, cudaMemcpyDeviceToHost));
         }
         if (bad) { set_err(err, errcap, msg); return bad; }
         return 0;
@@ -812,12 +1253,9 @@ int zke_witness(zke_ctx* x, const uint8_t* inputs, size_t batch, uint8_t* wtns_o
 
 int zke_load_witness(zke_ctx* x, const uint8_t* wtns, size_t batch, char* err, size_t errcap) {
     try {
-        if (!x) throw std::runtime_error("null context");
-        if (batch == 0 || batch > x->max_batch) throw std::runtime_error("batch exceeds the context's max_batch");
-        CUDA_OK(cudaSetDevice(x->device));
-        const size_t m = x->circuit->c.n_vars;
-        CUDA_OK(cudaMemcpy2D(x->w_all.p, x->stride * 32, wtns, m * 32, m * 32, batch, cudaMemcpyHostToDevice));
-        x->loaded = (uint32_t)batch;
+        if (!x || !wtns) throw std::runtime_error("null argument");
+        require_idle(x);
+        load_witness(x, x->slots[0], wtns, batch);
         return 0;
     } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
 }
@@ -825,8 +1263,56 @@ int zke_load_witness(zke_ctx* x, const uint8_t* wtns, size_t batch, char* err, s
 int zke_prove(zke_ctx* x, size_t batch, const uint8_t* rs, uint8_t* proofs_out, uint8_t* publics_out, int32_t* status, char* err, size_t errcap) {
     try {
         if (!x || !proofs_out) throw std::runtime_error("null argument");
+        require_idle(x);
         std::string msg;
-        int bad = do_prove(x, batch, rs, proofs_out, publics_out, status, msg);
+        int bad = do_prove(x, x->slots[0], batch, rs, proofs_out, publics_out, status, msg);
+        if (bad) { set_err(err, errcap, msg); return bad; }
+        return 0;
+    } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+
+int zke_wtns_prove(zke_ctx* x, const void* wtns_bytes, size_t len, const uint8_t* rs, uint8_t* proof_out, uint8_t* publics_out,
+                   char* err, size_t errcap) {
+    try {
+        if (!x || !proof_out) throw std::runtime_error("null argument");
+        require_idle(x);
+        const uint8_t* data = parse_wtns((const uint8_t*)wtns_bytes, len, x->n_vars);
+        load_witness(x, x->slots[0], data, 1);
+        std::string msg;
+        int32_t status = -1;
+        int bad = do_prove(x, x->slots[0], 1, rs, proof_out, publics_out, &status, msg);
+        if (bad) { set_err(err, errcap, msg); return bad; }
+        return 0;
+    } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+
+int zke_fullprove_submit(zke_ctx* x, const uint8_t* inputs, size_t batch, const uint8_t* rs, char* err, size_t errcap) {
+    try {
+        if (!x) throw std::runtime_error("null context");
+        if (x->profile) throw std::runtime_error("stage profiling needs the synchronous entry points");
+        if (x->n_submitted - x->n_collected >= 2) throw std::runtime_error("two batches are already in flight: collect one first");
+        CUDA_OK(cudaSetDevice(x->device));
+        zke_ctx::Slot& S = x->slots[x->n_submitted & 1];
+        alloc_slot(x, S);
+        try {
+            do_witness(x, S, inputs, batch);
+            enqueue_prove(x, S, batch, rs);
+        } catch (...) { sync_lanes(x); throw; }
+        S.busy = true;
+        x->n_submitted++;
+        return 0;
+    } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+
+int zke_fullprove_collect(zke_ctx* x, uint8_t* proofs_out, uint8_t* publics_out, int32_t* status, char* err, size_t errcap) {
+    try {
+        if (!x || !proofs_out) throw std::runtime_error("null argument");
+        if (x->n_submitted == x->n_collected) throw std::runtime_error("nothing was submitted");
+        zke_ctx::Slot& S = x->slots[x->n_collected & 1];
+        x->n_collected++;      // the slot is released whatever happens below
+        S.busy = false;
+        std::string msg;
+        int bad = finish_prove(x, S, proofs_out, publics_out, status, msg);
         if (bad) { set_err(err, errcap, msg); return bad; }
         return 0;
     } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
@@ -836,9 +1322,11 @@ int zke_fullprove(zke_ctx* x, const uint8_t* inputs, size_t batch, const uint8_t
                   int32_t* status, char* err, size_t errcap) {
     try {
         if (!x || !proofs_out) throw std::runtime_error("null argument");
-        do_witness(x, inputs, batch);
+        require_idle(x);
+        zke_ctx::Slot& S = x->slots[0];
+        do_witness(x, S, inputs, batch);
         std::string msg;
-        int bad = do_prove(x, batch, rs, proofs_out, publics_out, status, msg);
+        int bad = do_prove(x, S, batch, rs, proofs_out, publics_out, status, msg);
         if (bad) { set_err(err, errcap, msg); return bad; }
         return 0;
     } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }

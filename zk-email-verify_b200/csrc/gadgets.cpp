@@ -1,5 +1,7 @@
 #include "gadgets.hpp"
 #include <algorithm>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 
 namespace zke {
@@ -7,8 +9,13 @@ namespace gadgets {
 
 static const Fr& fr_one() { static const Fr o = Fr::one(); return o; }
 static Fr fr_pow2(uint32_t e) {
-    static std::vector<Fr> tab;
-    if (tab.empty()) { tab.resize(256); tab[0] = Fr::one(); for (int i = 1; i < 256; ++i) tab[i] = tab[i - 1] + tab[i - 1]; }
+    // built completely inside the initialiser: C++11 makes that thread-safe (zke_circuit_build may be called concurrently)
+    static const std::vector<Fr> tab = [] {
+        std::vector<Fr> t(256);
+        t[0] = Fr::one();
+        for (int i = 1; i < 256; ++i) t[i] = t[i - 1] + t[i - 1];
+        return t;
+    }();
     if (e >= 256) throw std::runtime_error("fr_pow2: exponent too large");
     return tab[e];
 }
@@ -627,9 +634,15 @@ LCVec fp_mul(Builder& b, uint32_t n, uint32_t k, const LCVec& x, const LCVec& y,
         v_t[xx] = b.signal(v_ab[xx] - v_pq_r);                                          // v_t[x] <== v_ab[x] - v_pq_r[x]
     }
     static std::map<uint32_t, std::vector<std::vector<Fr>>> interp_cache;
-    auto it = interp_cache.find(npts);
-    if (it == interp_cache.end()) it = interp_cache.emplace(npts, poly_interp_matrix(npts)).first;
-    const auto& M = it->second;
+    static std::mutex interp_mutex;          // zke_circuit_build is callable from several threads (ctypes drops the GIL)
+    const std::vector<std::vector<Fr>>* Mp;
+    {
+        std::lock_guard<std::mutex> lock(interp_mutex);
+        auto it = interp_cache.find(npts);
+        if (it == interp_cache.end()) it = interp_cache.emplace(npts, poly_interp_matrix(npts)).first;
+        Mp = &it->second;                    // std::map nodes are stable: later insertions do not move this entry
+    }
+    const auto& M = *Mp;
     LCVec t(npts);
     for (uint32_t j = 0; j < npts; ++j) {
         LC e;

@@ -7,7 +7,8 @@ namespace zke {
 namespace dev {
 
 // Term word y = coefficient index (bits 0-15) | k << 16 | kind << 24 with kind 0: +1, 1: -1, 2: +2^k, 3: -2^k,
-// 4: any other coefficient.  Kinds 0-3 are 97.6 % of the terms of EmailVerifier (bit / byte packings, the -2ab / 4abc
+// 4: any other coefficient - there the index takes bits 0-23 (a circom-compiled key may hold more than 2^16 distinct
+// coefficients; a +-2^k coefficient whose index does not fit 16 bits is simply encoded as kind 4).  Kinds 0-3 are 97.6 % of the terms of EmailVerifier (bit / byte packings, the -2ab / 4abc
 // terms of the SHA-256 gadgets): they need no Montgomery product - a power of two is a shift as long as x * 2^k stays
 // below 2^253 < r, which holds whenever x is the bit, byte or limb it is in these gadgets; otherwise (kind 4, or a
 // shifted value that would overflow) the term falls back to (c*R) (x) x with the Montgomery-scaled coefficient table.
@@ -50,7 +51,7 @@ __device__ __forceinline__ TermVal term_value(const uint8_t* coef_r, const uint2
     if (kind < TERM_KIND_POW2) { t.v = x; return t; }
     if (kind < TERM_KIND_GENERAL && bit_length(x) + k <= 253) { t.v = shl256(x, k); return t; }
     t.neg = false;
-    t.v = Fr::load(coef_r + 32ull * (term.y & 0xffffu)) * x;   // (c*R) (x) -> c*x, standard form
+    t.v = Fr::load(coef_r + 32ull * (term.y & (kind == TERM_KIND_GENERAL ? 0xffffffu : 0xffffu))) * x;   // (c*R) (x) -> c*x, standard form
     return t;
 }
 

@@ -30,9 +30,11 @@ build_ab_kernel(DevR1cs R, const uint8_t* __restrict__ w, uint8_t* __restrict__ 
     if (i < R.n_constraints) {
         a = row_dot(R.a_ptr, R.a_terms, R.coef_r, w, i);
         b = row_dot(R.b_ptr, R.b_terms, R.coef_r, w, i);
-        const Fr c_lc = row_dot(R.c_ptr, R.c_terms, R.coef_r, w, i);
         a = a.to_mont();
-        if ((a * b) != c_lc) atomicMin(first_bad, i);   // (aR) (x) b = a b in standard form
+        if (R.c_ptr) {   // contexts opened from a `.zkey` alone have no C matrix (snarkjs does not check either)
+            const Fr c_lc = row_dot(R.c_ptr, R.c_terms, R.coef_r, w, i);
+            if ((a * b) != c_lc) atomicMin(first_bad, i);   // (aR) (x) b = a b in standard form
+        }
         b = b.to_mont();
         if (c_out) c = a * b;
     } else if (i <= R.n_constraints + R.n_public) {
@@ -42,6 +44,23 @@ build_ab_kernel(DevR1cs R, const uint8_t* __restrict__ w, uint8_t* __restrict__ 
     a.store(a_out + 32ull * i);
     b.store(b_out + 32ull * i);
     if (c_out) c.store(c_out + 32ull * i);
+}
+
+// Validation of externally supplied witnesses (zke_load_witness): every value canonical (< r) and w[0] == 1.
+__global__ void check_witness_kernel(const uint8_t* __restrict__ w_all, size_t stride_elems, uint32_t n_vars, uint32_t batch, uint32_t* flag) {
+    const size_t total = (size_t)n_vars * batch;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t e = (uint32_t)(t / n_vars), i = (uint32_t)(t % n_vars);
+        Fr x = Fr::load(w_all + 32ull * (stride_elems * e + i));
+        Fr y = x;
+        y.reduce_once();
+        if (y != x) flag[0] = 1;
+        if (i == 0) { Fr one = Fr::zero(); one.v[0] = 1; if (x != one) flag[1] = 1; }
+    }
+}
+void launch_check_witness(const uint8_t* w_all, size_t stride_elems, uint32_t n_vars, uint32_t batch, uint32_t* flag, cudaStream_t st) {
+    check_witness_kernel<<<148 * 8, 256, 0, st>>>(w_all, stride_elems, n_vars, batch, flag);
+    ZKE_COUNT_LAUNCH(1);
 }
 
 void launch_build_ab(const DevR1cs& R, const uint8_t* w, uint8_t* a_out, uint8_t* b_out, uint8_t* c_out, uint32_t n, uint32_t* first_bad, cudaStream_t st) {

@@ -119,6 +119,16 @@ F12 miller_loop(const G2AffineH& q, const G1AffineH& p) {
         return l;
     };
     auto add_step = [&](const G2AffineH& s) {
+        // r == +-s cannot happen for a point of the order-r subgroup (the callers check membership); should it, the
+        // line degenerates - treat it like the tangent / vertical case instead of dividing by zero
+        if (s.x == r.x) {
+            if (s.y == r.y) return dbl_step();
+            F12 l = F12::zero();
+            l.c[0] = p.x;
+            add_fq2_term(l, r.x.neg(), 2);
+            r = G2AffineH::inf();
+            return l;
+        }
         Fq2 lambda = (s.y - r.y) * (s.x - r.x).inv();
         F12 l = line_eval(lambda, r, p);
         Fq2 x3 = lambda.sqr() - r.x - s.x;
@@ -158,13 +168,48 @@ F12 final_exponentiation(const F12& f) {
     return res;
 }
 
+F12 pow_u256(const F12& f, const U256& e) {
+    F12 res = F12::one();
+    for (int i = 255; i >= 0; --i) {
+        res = mul(res, res);
+        if (u256_bit(e, i)) res = mul(res, f);
+    }
+    return res;
+}
+
 }  // namespace
+
+// Order-r subgroup membership of a G2 point: BN254's G2 has a large cofactor, so the curve equation alone does not
+// imply it (ark-groth16, the Rust twin of this verifier, rejects such points on deserialisation).
+bool g2_in_subgroup(const G2AffineH& p) {
+    if (p.is_inf()) return true;
+    return G2JacH::from_affine(p).mul(fr_params().p).is_inf();
+}
+
+// vk_alphabeta_12 of `snarkjs zkey export verificationkey`: e(alpha_1, beta_2) as the Fq2-Fq6-Fq12 tower element
+// out[i][j][k] (Fq12 = Fq6[w]/(w^2 - v), Fq6 = Fq2[v]/(v^3 - (9 + u))), in standard form.  ffjavascript / wasmcurves
+// (like libff) finish the pairing with the Fuentes-Castaneda hard part, which yields the reduced pairing raised to
+// 2 z (6 z^2 + 3 z + 1), z = 4965661367192848881 - reproduced here; pinned on the reference's fixture
+// (/root/reference/packages/rust-verifier/tests/data/proof_of_twitter/vkey.json:43).
+void pairing_alphabeta(const G1AffineH& alpha1, const G2AffineH& beta2, U256 out[12]) {
+    static const U256 K = u256_from_hex("3bec47df15e307c81ea96b02d9d9e38d2e5d4e223ddedaf4");
+    const F12 e = pow_u256(final_exponentiation(miller_loop(beta2, alpha1)), K);
+    // dense sum c_n w^n with u = w^6 - 9  ->  tower coefficient (i, j) = (c[2j+i] + 9 c[2j+i+6]) + c[2j+i+6] u
+    const Fq nine = Fq::from_u64(9);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 3; ++j) {
+            const int n = 2 * j + i;
+            out[(i * 3 + j) * 2 + 0] = (e.c[n] + nine * e.c[n + 6]).to_u256();
+            out[(i * 3 + j) * 2 + 1] = e.c[n + 6].to_u256();
+        }
+}
 
 bool groth16_verify(const VerifyingKey& vk, const std::vector<U256>& publics, const Proof& pr) {
     if (publics.size() + 1 != vk.ic.size()) return false;
     for (auto& s : publics) if (u256_cmp(s, fr_params().p) >= 0) return false;
     if (!g1_on_curve(pr.a) || !g1_on_curve(pr.c) || !g2_on_curve(pr.b)) return false;
     if (!g1_on_curve(vk.alpha1) || !g2_on_curve(vk.beta2) || !g2_on_curve(vk.gamma2) || !g2_on_curve(vk.delta2)) return false;
+    if (!g2_in_subgroup(pr.b) || !g2_in_subgroup(vk.beta2) || !g2_in_subgroup(vk.gamma2) || !g2_in_subgroup(vk.delta2)) return false;
     G1JacH vkx = G1JacH::from_affine(vk.ic[0]);
     for (size_t i = 0; i < publics.size(); ++i) {
         if (!g1_on_curve(vk.ic[i + 1])) return false;

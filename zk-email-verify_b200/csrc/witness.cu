@@ -125,7 +125,14 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
     // constant one and inputs
     if (tid == 0) { Fr one = Fr::zero(); one.v[0] = 1; one.store(w); }
     const uint8_t* in = inputs + 32ull * P.n_inputs * email;
-    for (uint32_t i = tid; i < P.n_inputs; i += blockDim.x) Fr::load(in + 32ull * i).store(w + 32ull * (1 + P.n_outputs + i));
+    for (uint32_t i = tid; i < P.n_inputs; i += blockDim.x) {
+        // inputs cross the ABI as raw 32-byte integers: reduce them mod r the way snarkjs' witness calculator does
+        // (2^256 < 6 r, so at most five subtractions); everything downstream assumes canonical values
+        Fr x = Fr::load(in + 32ull * i);
+#pragma unroll 1
+        for (int k = 0; k < 5; ++k) x.reduce_once();
+        x.store(w + 32ull * (1 + P.n_outputs + i));
+    }
     if (P.n_iters == 0) return;
 
     // software pipeline: op records one iteration ahead (registers), term blocks one iteration ahead (cp.async into
@@ -178,14 +185,16 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
     }
 }
 
+static const size_t WITNESS_SMEM = 2 * (size_t)WITNESS_TERM_BUF * sizeof(uint2);   // 128 KB: above the 48 KB default
+
+// The opt-in to > 48 KB of dynamic shared memory is a per-device (per-context) function attribute: the engine calls
+// this from select_device() for every device it touches, and checks the result.
+cudaError_t configure_witness_kernel() {
+    return cudaFuncSetAttribute(witness_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WITNESS_SMEM);
+}
+
 void launch_witness(const DevProgram& P, uint8_t* w_all, size_t stride_elems, const uint8_t* inputs, uint32_t batch, cudaStream_t st) {
-    static const size_t smem = 2 * (size_t)WITNESS_TERM_BUF * sizeof(uint2);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(witness_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
-    witness_kernel<<<batch, WITNESS_THREADS, smem, st>>>(P, w_all, stride_elems, inputs, batch);
+    witness_kernel<<<batch, WITNESS_THREADS, WITNESS_SMEM, st>>>(P, w_all, stride_elems, inputs, batch);
     ZKE_COUNT_LAUNCH(1);
 }
 

@@ -61,6 +61,15 @@ c_u8p = ctypes.POINTER(ctypes.c_uint8)
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 zke_setup = _sig("zke_setup", c_void_p, [c_void_p, c_u64, c_int, c_char_p, c_size_t])
 zke_zkey_free = _sig("zke_zkey_free", None, [c_void_p])
+zke_zkey_load = _sig("zke_zkey_load", c_void_p, [c_void_p, c_size_t, c_int, c_char_p, c_size_t])
+zke_zkey_load_chunks = _sig("zke_zkey_load_chunks", c_void_p, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_size_t), c_size_t, c_int, c_char_p, c_size_t])
+zke_zkey_write = _sig("zke_zkey_write", c_i64, [c_void_p, c_void_p, c_void_p, c_size_t])
+zke_zkey_is_toy = _sig("zke_zkey_is_toy", c_int, [c_void_p])
+zke_circuit_build_regex = _sig("zke_circuit_build_regex", c_void_p, [ctypes.POINTER(c_char_p), c_char_p, c_size_t, c_u32, c_char_p, c_size_t])
+zke_fullprove_submit = _sig("zke_fullprove_submit", c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_char_p, c_size_t])
+zke_fullprove_collect = _sig("zke_fullprove_collect", c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_char_p, c_size_t])
+zke_wtns_prove = _sig("zke_wtns_prove", c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_char_p, c_size_t])
+zke_pairing_alphabeta = _sig("zke_pairing_alphabeta", c_int, [c_void_p, c_void_p, c_void_p])
 zke_zkey_info = _sig("zke_zkey_info", c_int, [c_void_p, ctypes.POINTER(c_u32), ctypes.POINTER(c_u32), ctypes.POINTER(c_u32)])
 zke_zkey_section = _sig("zke_zkey_section", c_i64, [c_void_p, c_int, c_void_p, c_size_t])
 zke_ctx_open = _sig("zke_ctx_open", c_void_p, [c_void_p, c_void_p, c_int, c_u32, c_char_p, c_size_t])

@@ -8,12 +8,14 @@ FR_MODULUS = 2188824287183927522224640574525727508854836440041603434369820418657
 
 
 class Circuit:
-    def __init__(self, template: str, params=()):
-        arr = (L.c_i64 * len(params))(*[int(p) for p in params])
-        err = ctypes.create_string_buffer(L.ERRCAP)
-        self._h = L.zke_circuit_build(template.encode(), arr, len(params), err, L.ERRCAP)
-        if not self._h:
-            raise L.ZkeError(err.value.decode())
+    def __init__(self, template: str, params=(), _handle=None):
+        if _handle is None:
+            arr = (L.c_i64 * len(params))(*[int(p) for p in params])
+            err = ctypes.create_string_buffer(L.ERRCAP)
+            _handle = L.zke_circuit_build(template.encode(), arr, len(params), err, L.ERRCAP)
+            if not _handle:
+                raise L.ZkeError(err.value.decode())
+        self._h = _handle
         self.template, self.params = template, tuple(params)
         info = L.CircuitInfo()
         L.zke_circuit_get_info(self._h, ctypes.byref(info))
@@ -24,6 +26,18 @@ class Circuit:
         for i in range(info.n_groups):
             L.zke_circuit_group(self._h, i, name, 256, ctypes.byref(first), ctypes.byref(count), ctypes.byref(kind))
             self.groups[name.value.decode()] = (first.value, count.value, kind.value)
+
+    @classmethod
+    def from_regex(cls, parts, msg_len: int):
+        """zk-regex circuit of a decomposed regex: parts = [(regex fragment, is_public), ...]; signals msg[msg_len] ->
+        out, reveal0[msg_len] (the generator behind BodyHashRegex, email-verifier.circom:5,126)."""
+        arr = (L.c_char_p * len(parts))(*[p.encode() for p, _ in parts])
+        pub = bytes(1 if q else 0 for _, q in parts)
+        err = ctypes.create_string_buffer(L.ERRCAP)
+        h = L.zke_circuit_build_regex(arr, pub, len(parts), msg_len, err, L.ERRCAP)
+        if not h:
+            raise L.ZkeError(err.value.decode())
+        return cls("Regex", (msg_len,), _handle=h)
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -16,12 +16,59 @@ def device_count() -> int:
 
 
 class Zkey:
-    def __init__(self, circuit: Circuit, seed: int = 1, device: int = 0):
-        err = ctypes.create_string_buffer(L.ERRCAP)
-        self._h = L.zke_setup(circuit.handle, seed, device, err, L.ERRCAP)
-        if not self._h:
-            raise L.ZkeError(err.value.decode())
+    """Groth16 proving key resident on one GPU.  `Zkey(circuit, seed)` runs the TOY seeded setup (known toxic waste:
+    tests and benchmarks only); `Zkey.load(bytes)` / `Zkey.load_chunks([...])` ingest a real snarkjs `.zkey`."""
+
+    def __init__(self, circuit: Circuit | None, seed: int = 1, device: int = 0, _handle=None):
+        if _handle is None:
+            err = ctypes.create_string_buffer(L.ERRCAP)
+            _handle = L.zke_setup(circuit.handle, seed, device, err, L.ERRCAP)
+            if not _handle:
+                raise L.ZkeError(err.value.decode())
+        self._h = _handle
         self.circuit, self.device = circuit, device
+
+    @classmethod
+    def load(cls, zkey_bytes: bytes, device: int = 0, circuit: Circuit | None = None):
+        """`${circuitName}.zkey` as handed to snarkjs.groth16.fullProve (chunked-zkey.ts:80-84)."""
+        err = ctypes.create_string_buffer(L.ERRCAP)
+        h = L.zke_zkey_load(zkey_bytes, len(zkey_bytes), device, err, L.ERRCAP)
+        if not h:
+            raise L.ZkeError(err.value.decode())
+        return cls(circuit, device=device, _handle=h)
+
+    @classmethod
+    def load_chunks(cls, chunks, device: int = 0, circuit: Circuit | None = None):
+        """The fork's chunked key: chunks[i] = contents of `${circuitName}.zkey{b..k}[i]` (chunked-zkey.ts:9,35-37)."""
+        keep = [bytes(c) for c in chunks]
+        ptrs = (L.c_void_p * len(keep))(*[ctypes.cast(ctypes.c_char_p(c), L.c_void_p) for c in keep])
+        lens = (L.c_size_t * len(keep))(*[len(c) for c in keep])
+        err = ctypes.create_string_buffer(L.ERRCAP)
+        h = L.zke_zkey_load_chunks(ptrs, lens, len(keep), device, err, L.ERRCAP)
+        if not h:
+            raise L.ZkeError(err.value.decode())
+        return cls(circuit, device=device, _handle=h)
+
+    @property
+    def is_toy(self) -> bool:
+        return L.zke_zkey_is_toy(self._h) == 1
+
+    @property
+    def info(self):
+        a, b, c = L.c_u32(), L.c_u32(), L.c_u32()
+        L.zke_zkey_info(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c))
+        return {"n_vars": a.value, "n_public": b.value, "domain_log2": c.value}
+
+    def write(self) -> bytes:
+        """The key as a `.zkey` file image (iden3 binfile, what `snarkjs groth16 setup` writes)."""
+        ch = self.circuit.handle if self.circuit is not None else None
+        n = L.zke_zkey_write(self._h, ch, None, 0)
+        if n < 0:
+            raise L.ZkeError("zkey export failed (a key made by the toy setup needs its circuit)")
+        buf = ctypes.create_string_buffer(n)
+        if L.zke_zkey_write(self._h, ch, buf, n) != n:
+            raise L.ZkeError("zkey export failed")
+        return buf.raw
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -54,12 +101,16 @@ class Zkey:
 
 
 class Context:
-    def __init__(self, circuit: Circuit, zkey: Zkey | None = None, device: int = 0, max_batch: int = 1):
+    def __init__(self, circuit: Circuit | None, zkey: Zkey | None = None, device: int = 0, max_batch: int = 1):
         err = ctypes.create_string_buffer(L.ERRCAP)
-        self._h = L.zke_ctx_open(circuit.handle, zkey.handle if zkey else None, device, max_batch, err, L.ERRCAP)
+        self._h = L.zke_ctx_open(circuit.handle if circuit is not None else None, zkey.handle if zkey else None, device,
+                                 max_batch, err, L.ERRCAP)
         if not self._h:
             raise L.ZkeError(err.value.decode())
         self.circuit, self.zkey, self.device, self.max_batch = circuit, zkey, device, max_batch
+        self._pending = []
+        self.n_vars = circuit.info.n_vars if circuit is not None else zkey.info["n_vars"]
+        self.n_public = circuit.info.n_public if circuit is not None else zkey.info["n_public"]
 
     def close(self):
         if getattr(self, "_h", None):
@@ -92,7 +143,7 @@ class Context:
 
     def witness(self, packed_inputs, batch: int, want_witness: bool = True, raise_on_fail: bool = True):
         """calculateWitness + checkConstraints.  Returns (witness bytes | None, status list)."""
-        m = self.circuit.info.n_vars
+        m = self.n_vars
         out = ctypes.create_string_buffer(32 * m * batch) if want_witness else None
         status = (ctypes.c_int32 * batch)()
         err = ctypes.create_string_buffer(L.ERRCAP)
@@ -109,7 +160,7 @@ class Context:
             raise L.ZkeError(err.value.decode())
 
     def _prove_call(self, fn, head_args, batch, rs, raise_on_fail):
-        npub = self.circuit.info.n_public
+        npub = self.n_public
         proofs = ctypes.create_string_buffer(256 * batch)
         publics = ctypes.create_string_buffer(max(1, 32 * npub * batch))
         status = (ctypes.c_int32 * batch)()
@@ -124,8 +175,40 @@ class Context:
     def prove(self, batch: int, rs: bytes | None = None, raise_on_fail: bool = True):
         return self._prove_call(L.zke_prove, (), batch, rs, raise_on_fail)
 
+    def wtns_prove(self, wtns_file: bytes, rs: bytes | None = None):
+        """`snarkjs groth16 prove zkey wtns`: one `.wtns` file image -> (proof bytes, public signal bytes)."""
+        npub = self.n_public
+        proof = ctypes.create_string_buffer(256)
+        publics = ctypes.create_string_buffer(max(1, 32 * npub))
+        err = ctypes.create_string_buffer(L.ERRCAP)
+        rc = L.zke_wtns_prove(self._h, wtns_file, len(wtns_file), rs, proof, publics, err, L.ERRCAP)
+        if rc != 0:
+            raise L.ZkeError(err.value.decode())
+        return proof.raw, publics.raw[: 32 * npub]
+
+    def submit(self, packed_inputs, batch: int, rs: bytes | None = None):
+        """Pipelined fullprove: enqueue one batch (at most two in flight); pair with collect()."""
+        err = ctypes.create_string_buffer(L.ERRCAP)
+        if L.zke_fullprove_submit(self._h, packed_inputs, batch, rs, err, L.ERRCAP) != 0:
+            raise L.ZkeError(err.value.decode())
+        self._pending.append(batch)
+
+    def collect(self, raise_on_fail: bool = True):
+        batch = self._pending.pop(0)
+        npub = self.n_public
+        proofs = ctypes.create_string_buffer(256 * batch)
+        publics = ctypes.create_string_buffer(max(1, 32 * npub * batch))
+        status = (ctypes.c_int32 * batch)()
+        err = ctypes.create_string_buffer(L.ERRCAP)
+        rc = L.zke_fullprove_collect(self._h, proofs, publics, status, err, L.ERRCAP)
+        if rc < 0:
+            raise L.ZkeError(err.value.decode())
+        if rc > 0 and raise_on_fail:
+            raise AssertFailed(err.value.decode())
+        return proofs.raw, publics.raw[: 32 * npub * batch], list(status)
+
     def fullprove(self, packed_inputs, batch: int, rs: bytes | None = None, raise_on_fail: bool = True):
-        npub = self.circuit.info.n_public
+        npub = self.n_public
         proofs = ctypes.create_string_buffer(256 * batch)
         publics = ctypes.create_string_buffer(max(1, 32 * npub * batch))
         status = (ctypes.c_int32 * batch)()

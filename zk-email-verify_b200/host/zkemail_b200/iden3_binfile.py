@@ -194,12 +194,15 @@ def zkey_sections(zkey) -> dict[int, bytes]:
 
 
 def write_zkey(zkey) -> bytes:
-    return _write_container(b"zkey", 1, sorted(zkey_sections(zkey).items()))
+    """`.zkey` file image, written natively by the engine (zke_zkey_write); zkey_sections() above is the Python
+    restatement of the same layout, kept for small circuits and as a cross-check of the native writer."""
+    return zkey.write()
 
 
 def write_zkey_chunks(zkey) -> dict[str, bytes]:
     """The fork's chunked layout: `${name}.zkey{b..k}` holds section 1..10 (chunked-zkey.ts:9)."""
-    return {"zkey" + ZKEY_CHUNK_SUFFIXES[s - 1]: payload for s, payload in zkey_sections(zkey).items()}
+    _, sec = read_container(zkey.write(), b"zkey")
+    return {"zkey" + ZKEY_CHUNK_SUFFIXES[s - 1]: payload for s, payload in sec.items()}
 
 
 def read_zkey(blob: bytes) -> dict:
