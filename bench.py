@@ -7,7 +7,10 @@ proof).  One "step" = one pass of the hot path over one batch.  With N GPUs ever
 (weak scaling, no data-path collective - SURVEY 8(e)(i)); the ranks only meet at the timing barrier.
 
   value  : whole-job proofs/s with the packed inputs already resident in HBM when the timed region starts
-  e2e    : the same through the C-ABI call zke_fullprove with pinned HOST buffers (H2D of inputs, D2H of proofs inside)
+  e2e    : the same through the C-ABI with pinned HOST buffers (H2D of inputs, D2H of proofs inside the timed region)
+  Both arms drive the K timed steps through the pipelined form of fullprove (zke_fullprove_submit / _collect, at most
+  two batches in flight): the latency-bound witness kernel of step k + 1 runs under the proving kernels of step k.
+  Every step's witness + proving work, its copies and its host tail lie inside the timed region.
   roofline: the dominant kernel (bucket accumulation of the H multi-exponentiation) timed live with CUDA events;
             achieved = algorithmic bytes (N x (64-byte point + 32-byte scalar)) / kernel time vs the
             measured HBM copy peak.  The kernel is bound by the integer (IMAD) pipe, not HBM - see DESIGN.md.
@@ -177,6 +180,22 @@ def main():
         if rc != 0:
             raise RuntimeError("zke_fullprove failed: %d %s" % (rc, err.value.decode()))
 
+    def submit(inputs_ptr):
+        if L.zke_fullprove_submit(ctx.handle, inputs_ptr, batch, None, err, 4096) != 0:
+            raise RuntimeError("zke_fullprove_submit failed: %s" % err.value.decode())
+
+    def collect():
+        rc = L.zke_fullprove_collect(ctx.handle, pinned_proofs.data_ptr(), pinned_pub.data_ptr(), status, err, 4096)
+        if rc != 0:
+            raise RuntimeError("zke_fullprove_collect failed: %d %s" % (rc, err.value.decode()))
+
+    def pipelined(inputs_ptr, steps):
+        submit(inputs_ptr)
+        for _ in range(steps - 1):
+            submit(inputs_ptr)
+            collect()
+        collect()
+
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
@@ -187,8 +206,7 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(steps):
-            step(inputs_ptr)
+        pipelined(inputs_ptr, steps)
         e1.record(stream)
         e1.synchronize()
         ms = e0.elapsed_time(e1)
@@ -220,6 +238,32 @@ def main():
     step(None)
     prof = ctx.profile_get()
     ctx.profile(False)
+    # ---- extra lines (not part of `value`): BASELINE configs[1] = witness generation only for the same batch, and the
+    #      latency of a single-email fullProve (the reference's generateProof is a one-email call)
+    extra = {}
+    if rank == 0:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            rc = L.zke_witness(ctx.handle, None, batch, None, status, err, 4096)
+            if rc != 0:
+                raise RuntimeError("zke_witness failed: %s" % err.value.decode())
+        dtw = (time.perf_counter() - t0) / reps
+        lat = []
+        one_in = pinned_in.data_ptr()
+        for _ in range(5):
+            t0 = time.perf_counter()
+            rc = L.zke_fullprove(ctx.handle, one_in, 1, None, pinned_proofs.data_ptr(), pinned_pub.data_ptr(), status, err, 4096)
+            if rc != 0:
+                raise RuntimeError("zke_fullprove failed: %s" % err.value.decode())
+            lat.append(time.perf_counter() - t0)
+        lat.sort()
+        extra = {"config1_witness_only": {"workload": "configs[1]: batch of %d, calculateWitness + checkConstraints (zke_witness), inputs resident" % batch,
+                                          "emails_per_s": batch / dtw, "ms_per_batch": 1e3 * dtw,
+                                          "witness_kernel_ms_per_batch": prof["witness"]["ms"] / max(1, prof["witness"]["count"])},
+                 "single_email_fullprove_latency_ms": {"median": 1e3 * lat[len(lat) // 2], "min": 1e3 * lat[0],
+                                                       "what": "zke_fullprove(batch = 1) with host buffers, wall clock"}}
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -249,6 +293,19 @@ def main():
                 "note": "bound by the integer multiply pipe, not HBM: 13 windows x ~10 Fq products per 64-byte point "
                         "(fmaheavy pipe 85 % busy in the ncu capture); traffic = 13 table levels gathered at 64 B per "
                         "entry, see DESIGN.md section 5"}
+    # the pipe that actually bounds the kernel: integer multiply (IMAD.WIDE).  achieved = executed fmaheavy warp
+    # instructions of one launch (ncu capture, profiles/roofline_traffic.json) / live kernel time; peak = the measured
+    # IMAD.WIDE issue rate of this GPU (scripts/pipe_peaks.cu -> profiles/pipe_peaks_r02.json)
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            t = json.load(f)
+        with open(os.path.join(ROOT, "profiles", "pipe_peaks_r02.json")) as f:
+            pk = json.load(f)["results"]["imad_wide"]["giga_warp_instr_per_s"]
+        ach = float(t["fmaheavy_warp_instr"]) / (kernel_ms / 1e3) / 1e9
+        roofline["imad"] = {"achieved": ach, "peak": pk, "unit": "G warp-IMAD.WIDE/s", "frac": ach / pk,
+                            "warp_instr_per_launch": float(t["fmaheavy_warp_instr"])}
+    except Exception:
+        roofline["imad"] = None
     stages = {k: (v["ms"] / max(1, v["count"])) for k, v in prof.items()}
 
     cpu_baseline = None
@@ -269,7 +326,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": len(packed),
                     "d2h_bytes_per_step": 256 * batch + 32 * npub * batch + 4 * batch},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "stage_ms": stages}
+            "stage_ms": stages, "extra": extra,
+            "pipelining": "steps driven through zke_fullprove_submit/_collect, <= 2 batches in flight"}
     print(json.dumps(line))
     return 0
 
