@@ -5,6 +5,16 @@ using namespace zke::dev;
 extern "C" {
 void ff_set_consts(const uint32_t* mod, const uint32_t* r, const uint32_t* r2, uint32_t inv) {
     memcpy(FR_C.mod, mod, 32); memcpy(FR_C.r, r, 32); memcpy(FR_C.r2, r2, 32); FR_C.inv = inv;
+    uint64_t borrow = 0;   // nmod = 2^256 - mod
+    for (int i = 0; i < 8; ++i) { uint64_t d = (uint64_t)0 - mod[i] - borrow; FR_C.nmod[i] = (uint32_t)d; borrow = (d >> 32) & 1; }
+}
+// fixed-operand product: out = a * w mod p for w given as (standard form, floor(w 2^256 / p))
+void ff_shoup(const uint32_t* a, const uint32_t* w, const uint32_t* wq, uint32_t* out, int n) {
+    for (int i = 0; i < n; ++i) {
+        Fr x; memcpy(x.v, a + 8 * i, 32);
+        Fr z = Fr::mul_shoup(x, w + 8 * i, wq + 8 * i);
+        memcpy(out + 8 * i, z.v, 32);
+    }
 }
 static void run(int which, const uint32_t* a, const uint32_t* b, uint32_t* out) {
     Fr x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32);

@@ -72,6 +72,39 @@ def _check(mod, name):
         assert not bad, "%s %s: %d/%d wrong" % (name, nm, bad, n2)
 
 
+def _check_shoup(mod, name):
+    """mul_shoup(a, w, floor(w 2^256 / p)) == a * w mod p for every a < 2^256 (not only reduced ones) and w < p."""
+    R = 1 << 256
+    inv = (-pow(mod, -1, 1 << 32)) % (1 << 32)
+    lib.ff_set_consts(arr([mod]), arr([R % mod]), arr([R*R % mod]), ctypes.c_uint32(inv))
+    rnd = random.Random(7)
+    edge_a = [0, 1, 2, mod - 1, mod, mod + 1, 2 * mod, 3 * mod, R - 1, R - 2, (1 << 255), (1 << 224) - 1, (1 << 192), 0xffffffff, (1 << 32)]
+    edge_w = [0, 1, 2, mod - 1, mod - 2, mod >> 1, (1 << 253), (1 << 128) - 1, 0xffffffff, 3]
+    A, W = [], []
+    for a in edge_a:
+        for w in edge_w:
+            A.append(a); W.append(w)
+    for _ in range(6000):
+        A.append(rnd.randrange(R)); W.append(rnd.randrange(mod))
+    for _ in range(500):      # operands with long runs of ones / zeros: worst cases for the truncated quotient estimate
+        a = rnd.choice([R - 1, R - 1 - rnd.getrandbits(rnd.randrange(1, 200)), rnd.getrandbits(rnd.randrange(1, 256))])
+        w = rnd.choice([mod - 1 - rnd.getrandbits(rnd.randrange(1, 200)), rnd.getrandbits(rnd.randrange(1, 253))]) % mod
+        A.append(a % R); W.append(w)
+    n = len(A)
+    WQ = [(w << 256) // mod for w in W]
+    assert max(WQ) < R
+    out = (ctypes.c_uint32 * (8 * n))()
+    lib.ff_shoup(arr(A), arr(W), arr(WQ), out, n)
+    got = unarr(out, 8, n)
+    bad = [i for i in range(n) if got[i] != A[i] * W[i] % mod]
+    assert not bad, "%s mul_shoup: %d/%d wrong, first a=%x w=%x got=%x" % (name, len(bad), n, A[bad[0]], W[bad[0]], got[bad[0]])
+
+
+def test_fr_shoup_product():
+    _check_shoup(P, "Fr")
+    _check_shoup(Q, "Fq")
+
+
 def test_fr_arithmetic():
     _check(P, "Fr")
 

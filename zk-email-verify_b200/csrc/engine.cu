@@ -52,7 +52,43 @@ struct DevBuf {
 void fill_consts(dev::FieldConsts& c, const FieldParams& p) {
     memcpy(c.mod, p.p.v, 32); memcpy(c.r, p.r.v, 32); memcpy(c.r2, p.r2.v, 32);
     c.inv = (uint32_t)p.inv;
+    U256 zero = {{0, 0, 0, 0}}, n;
+    u256_sub(n, zero, p.p);          // 2^256 - p
+    memcpy(c.nmod, n.v, 32);
 }
+
+// Fixed-operand form of a constant w (ff.cuh: Fp::mul_shoup): {w in standard form, floor(w 2^256 / r)}.  With
+// w 2^256 = q r + rem the remainder is the Montgomery image of w, so q = (w 2^256 - rem) / r exactly, and an exact
+// quotient is a product with r^-1 modulo 2^256: q = rem * (-r^-1 mod 2^256) mod 2^256 - no division.
+struct ShoupPair { U256 w, wq; };
+U256 mul_lo256(const U256& a, const U256& b) {
+    uint64_t t[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) {
+        u128 c = 0;
+        for (int j = 0; i + j < 4; ++j) {
+            c += (u128)a.v[j] * b.v[i] + t[i + j];
+            t[i + j] = (uint64_t)c;
+            c >>= 64;
+        }
+    }
+    return U256{{t[0], t[1], t[2], t[3]}};
+}
+const U256& fr_neg_inv256() {     // -r^-1 mod 2^256 (Newton iteration from the 64-bit constant of the Montgomery product)
+    static const U256 v = [] {
+        const U256& p = fr_params().p;
+        U256 y = {{(uint64_t)0 - fr_params().inv, 0, 0, 0}};          // r^-1 mod 2^64
+        for (int it = 0; it < 2; ++it) {                               // y <- y (2 - r y): 64 -> 128 -> 256 bits
+            U256 t = mul_lo256(p, y), two = {{2, 0, 0, 0}}, d;
+            u256_sub(d, two, t);
+            y = mul_lo256(y, d);
+        }
+        U256 zero = {{0, 0, 0, 0}}, n;
+        u256_sub(n, zero, y);
+        return n;
+    }();
+    return v;
+}
+ShoupPair shoup_pair(const Fr& w) { return ShoupPair{w.to_u256(), mul_lo256(w.m, fr_neg_inv256())}; }
 
 void select_device(int device) {
     int n = 0;
@@ -724,7 +760,7 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         const Fr omega = fr_root_of_unity(log_n), omega_inv = omega.inv();
         const Fr g = fr_root_of_unity(log_n + 1);
         const Fr n_inv = Fr::from_u64(N).inv();
-        std::vector<Fr> fw(std::max<size_t>(1, N / 2)), iv(std::max<size_t>(1, N / 2)), cs(N);
+        std::vector<ShoupPair> fw(std::max<size_t>(1, N / 2)), iv(std::max<size_t>(1, N / 2)), cs(N);
         const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
         std::vector<std::thread> th;
         for (unsigned t = 0; t < T; ++t) {
@@ -733,7 +769,7 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                 if (beg < end) {
                     U256 e = {{(uint64_t)beg, 0, 0, 0}};
                     Fr a = omega.pow(e), b = omega_inv.pow(e);
-                    for (size_t i = beg; i < end; ++i) { fw[i] = a; iv[i] = b; a = a * omega; b = b * omega_inv; }
+                    for (size_t i = beg; i < end; ++i) { fw[i] = shoup_pair(a); iv[i] = shoup_pair(b); a = a * omega; b = b * omega_inv; }
                 }
                 beg = N * t / T; end = N * (t + 1) / T;
                 if (beg < end) {
@@ -742,14 +778,14 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                     for (size_t j = beg; j < end; ++j) {
                         size_t p = 0;
                         for (unsigned bit = 0; bit < log_n; ++bit) if (j & ((size_t)1 << bit)) p |= (size_t)1 << (log_n - 1 - bit);
-                        cs[p] = a;
+                        cs[p] = shoup_pair(a);
                         a = a * g;
                     }
                 }
             });
         }
         for (auto& t : th) t.join();
-        if (N == 1) { fw[0] = Fr::one(); iv[0] = Fr::one(); }
+        if (N == 1) { fw[0] = shoup_pair(Fr::one()); iv[0] = shoup_pair(Fr::one()); }
         x->tw_fwd.upload(fw); x->tw_inv.upload(iv); x->coset_scale.upload(cs);
         x->ntt.tw_fwd = x->tw_fwd.p; x->ntt.tw_inv = x->tw_inv.p; x->ntt.log_n = (int)log_n;
         x->cfg_w = dev::msm_config_witness();

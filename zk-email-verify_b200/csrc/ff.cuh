@@ -30,6 +30,7 @@ struct FieldConsts {
     uint32_t r[8];    // 2^256 mod p  (Montgomery one)
     uint32_t r2[8];   // 2^512 mod p
     uint32_t inv;     // -p^-1 mod 2^32
+    uint32_t nmod[8]; // 2^256 - p  (the modulus negated mod 2^256: fixed-operand products accumulate a*w + q*(-p))
 };
 // One copy per translation unit (whole-program device compilation, no -rdc): every .cu that uses field arithmetic
 // instantiates ZKE_DEFINE_CONSTANT_UPLOAD(name) and the engine calls each TU's upload function once per device.
@@ -81,6 +82,8 @@ __device__ __forceinline__ void pair_madc_cc_new(uint32_t& lo, uint32_t& hi, uin
 __device__ __forceinline__ void pair_madc_last(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {      // {hi,lo} = a*b + CC ; no CC out
     asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
 }
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }                 // low word of a*b + c
+__device__ __forceinline__ uint32_t madc_lo(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("madc.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }   // + CC
 #else
 static inline uint32_t zke_add3(uint32_t a, uint32_t b, uint32_t c, bool set) { uint64_t s = (uint64_t)a + b + c; if (set) zke_cc = (uint32_t)(s >> 32); return (uint32_t)s; }
 static inline uint32_t add_cc(uint32_t a, uint32_t b) { return zke_add3(a, b, 0, true); }
@@ -101,6 +104,8 @@ static inline void pair_mad_cc_lo(uint32_t& lo, uint32_t& hi, uint32_t a, uint32
 static inline void pair_madc_cc_lo(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { lo = zke_add3(zke_lo(a, b), lo, zke_cc, true); hi = zke_add3(zke_hi(a, b), 0, zke_cc, true); }
 static inline void pair_madc_cc_new(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { lo = zke_add3(zke_lo(a, b), 0, zke_cc, true); hi = zke_add3(zke_hi(a, b), 0, zke_cc, true); }
 static inline void pair_madc_last(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { lo = zke_add3(zke_lo(a, b), 0, zke_cc, true); hi = zke_add3(zke_hi(a, b), 0, zke_cc, false); }
+static inline uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+static inline uint32_t madc_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c + zke_cc; }
 #endif
 
 template <class Tag>
@@ -552,6 +557,90 @@ struct Fp {
         return sqr_cios(*this);
 #endif
     }
+    // ---- fixed-operand (Shoup / Barrett) product a * w mod p for a CONSTANT w ------------------------------------
+    // w is given in standard form together with wq = floor(w * 2^256 / p) (precomputed per constant: NTT twiddles,
+    // coset factors).  With q ~ floor(a * wq / 2^256) the value a*w - q*p lies in [0, 3p) and p < 2^254, so it is
+    // determined by its low 256 bits: no reduction rows at all, only
+    //   - the upper part of a * wq, from the 43 limb products of weight >= 2^(32*6) (the dropped ones sum to less
+    //     than 2^229: q is at most one below the exact quotient digit, which the [0, 3p) range absorbs),
+    //   - the low halves of a * w and q * (2^256 - p): 2 x (28 full + 8 low-word) limb products,
+    // i.e. 99 IMAD.WIDE + 16 IMAD instead of the 136 IMAD.WIDE of the interleaved Montgomery product.  The result is
+    // a*w mod p exactly, for ANY a < 2^256: if a is in Montgomery form (x R), so is the result (x w R) - the data of
+    // the transforms stays in Montgomery form and only the constants change representation.
+    // low-half accumulation row: ev[k] <-> limb k, od[k] <-> limb k + 1; adds X[j] * y for i + j <= 7 (j = 7 - i: low word)
+    template <int I, bool FIRST>
+    static __device__ __forceinline__ void lo_row(uint32_t* ev, uint32_t* od, const uint32_t* X, uint32_t y) {
+        constexpr int PE = (I & 1) ? I + 1 : I;          // first even limb position of this row
+        constexpr int JE = (I & 1) ? 1 : 0;              // and the X index that lands there
+        constexpr int NE = (8 - PE) / 2;                 // full pairs into ev (positions PE, PE + 2, .., 6)
+        constexpr int PO = (I & 1) ? I : I + 1;          // first odd limb position
+        constexpr int JO = (I & 1) ? 0 : 1;
+        constexpr int NO = (7 - PO) / 2;                 // full pairs into od (positions PO .. 5)
+        if (FIRST) {
+#pragma unroll
+            for (int t = 0; t < NE; ++t) pair_mul(ev[PE + 2 * t], ev[PE + 2 * t + 1], X[JE + 2 * t], y);
+#pragma unroll
+            for (int t = 0; t < NO; ++t) pair_mul(od[PO - 1 + 2 * t], od[PO + 2 * t], X[JO + 2 * t], y);
+            od[6] = X[7 - I] * y;
+        } else {
+#pragma unroll
+            for (int t = 0; t < NE; ++t) {
+                if (t == 0) pair_mad_cc(ev[PE], ev[PE + 1], X[JE], y);
+                else pair_madc_cc(ev[PE + 2 * t], ev[PE + 2 * t + 1], X[JE + 2 * t], y);
+            }
+            // the carry out of limb 7 is dropped (arithmetic mod 2^256); a new chain starts for the odd positions
+#pragma unroll
+            for (int t = 0; t < NO; ++t) {
+                if (t == 0) pair_mad_cc(od[PO - 1], od[PO], X[JO], y);
+                else pair_madc_cc(od[PO - 1 + 2 * t], od[PO + 2 * t], X[JO + 2 * t], y);
+            }
+            od[6] = NO > 0 ? madc_lo(X[7 - I], y, od[6]) : mad_lo(X[7 - I], y, od[6]);
+        }
+    }
+    static __device__ __forceinline__ Fp mul_shoup(const Fp& a_in, const uint32_t* w, const uint32_t* wq) {
+        const FieldConsts& C = Tag::C();
+        const uint32_t* a = a_in.v;
+        // ---- q = upper half of a * wq (limb products of weight >= 6 only); local index k <-> limb 6 + k (ev), 7 + k (od)
+        uint32_t hev[10], hod[10];
+        int ee = 0, eo = 0;
+        ee = chain<1>(hev, ee, 0, a, 6, 2, wq[0]);  eo = chain<1>(hod, eo, 0, a, 7, 2, wq[0]);
+        eo = chain<1>(hod, eo, 0, a, 6, 2, wq[1]);  ee = chain<2>(hev, ee, 0, a, 5, 2, wq[1]);
+        ee = chain<2>(hev, ee, 0, a, 4, 2, wq[2]);  eo = chain<2>(hod, eo, 0, a, 5, 2, wq[2]);
+        eo = chain<2>(hod, eo, 0, a, 4, 2, wq[3]);  ee = chain<3>(hev, ee, 0, a, 3, 2, wq[3]);
+        ee = chain<3>(hev, ee, 0, a, 2, 2, wq[4]);  eo = chain<3>(hod, eo, 0, a, 3, 2, wq[4]);
+        eo = chain<3>(hod, eo, 0, a, 2, 2, wq[5]);  ee = chain<4>(hev, ee, 0, a, 1, 2, wq[5]);
+        ee = chain<4>(hev, ee, 0, a, 0, 2, wq[6]);  eo = chain<4>(hod, eo, 0, a, 1, 2, wq[6]);
+        eo = chain<4>(hod, eo, 0, a, 0, 2, wq[7]);  ee = chain<4>(hev, ee, 2, a, 1, 2, wq[7]);
+        uint32_t q[8];
+        {
+            // limb 7: hev[1] + hod[0] only contributes its carry; limbs 8..15 are q
+            (void)add_cc(hev[1], hod[0]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t e = (k + 2) < ee ? hev[k + 2] : 0, o = (k + 1) < eo ? hod[k + 1] : 0;
+                q[k] = k < 7 ? addc_cc(e, o) : addc(e, o);
+            }
+        }
+        // ---- r = low 256 bits of a * w + q * (2^256 - p)
+        uint32_t ev[8], od[8];
+        lo_row<0, true>(ev, od, a, w[0]);
+        lo_row<1, false>(ev, od, a, w[1]); lo_row<2, false>(ev, od, a, w[2]); lo_row<3, false>(ev, od, a, w[3]);
+        lo_row<4, false>(ev, od, a, w[4]); lo_row<5, false>(ev, od, a, w[5]); lo_row<6, false>(ev, od, a, w[6]);
+        lo_row<7, false>(ev, od, a, w[7]);
+        lo_row<0, false>(ev, od, q, C.nmod[0]); lo_row<1, false>(ev, od, q, C.nmod[1]); lo_row<2, false>(ev, od, q, C.nmod[2]);
+        lo_row<3, false>(ev, od, q, C.nmod[3]); lo_row<4, false>(ev, od, q, C.nmod[4]); lo_row<5, false>(ev, od, q, C.nmod[5]);
+        lo_row<6, false>(ev, od, q, C.nmod[6]); lo_row<7, false>(ev, od, q, C.nmod[7]);
+        Fp r;
+        r.v[0] = ev[0];
+        r.v[1] = add_cc(ev[1], od[0]);
+#pragma unroll
+        for (int k = 2; k < 7; ++k) r.v[k] = addc_cc(ev[k], od[k - 1]);
+        r.v[7] = addc(ev[7], od[6]);
+        r.reduce_once();
+        r.reduce_once();
+        return r;
+    }
+
     __device__ __forceinline__ Fp to_mont() const { return *this * r2(); }
     __device__ __forceinline__ Fp from_mont() const {
         Fp o = zero(); o.v[0] = 1;

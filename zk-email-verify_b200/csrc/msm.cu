@@ -14,7 +14,7 @@
 // (~300 IMAD each) per 64-byte point (SURVEY 8(d) "Which roofline bounds what").
 #include "device_engine.cuh"
 #include "msm.cuh"
-#include "ba.cuh"
+#include "msm_ba.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -305,136 +305,6 @@ chunk_sum_kernel(const uint8_t* __restrict__ points, const uint32_t* __restrict_
     }
 }
 
-// ---------------------------------------------------------------- batched-affine bucket accumulation
-// Same work split as chunk_sum_kernel (one thread per chunk of at most 256 bucket entries, output = the chunk's sum as
-// an XYZZ point), but the first NLEV levels of each chunk's addition tree are done in affine coordinates with a
-// batch inversion shared by the whole thread block (ba.cuh): level 0 adds the table points pairwise, level 1 the
-// level-0 sums, ...; what is left after NLEV levels (1/2^NLEV of the entries) is accumulated with XYZZ mixed additions.
-// Products per bucket of 104 entries: 78 x 6 + 26 x 10 + ~30 (block scans) = ~760 for NLEV = 2, against 1040.
-// Intermediate sums and prefix products live in per-thread local memory (20 KB, L2 / HBM backed).
-static const int BA_BLOCK = 128;
-
-// v = 1 / run for every thread of the block, with ONE field inversion: inclusive prefix and suffix product scans of
-// the threads' values in shared memory, the last thread inverts the grand total, then 1/run_t = ginv * E_t * S_t
-template <class F>
-__device__ __forceinline__ F block_batch_inverse(const F& run, F (*sh)[BA_BLOCK], F* ginv) {
-    const int t = threadIdx.x;
-    sh[0][t] = run;
-    sh[1][BA_BLOCK - 1 - t] = run;
-    __syncthreads();
-    for (int off = 1; off < BA_BLOCK; off <<= 1) {
-        F a, b;
-        const bool act = t >= off;
-        if (act) { a = sh[0][t - off]; b = sh[1][t - off]; }
-        __syncthreads();
-        if (act) { sh[0][t] = sh[0][t] * a; sh[1][t] = sh[1][t] * b; }
-        __syncthreads();
-    }
-    if (t == BA_BLOCK - 1) *ginv = sh[0][BA_BLOCK - 1].inv();
-    __syncthreads();
-    F v = *ginv;
-    if (t > 0) v = v * sh[0][t - 1];                          // product of the threads before t
-    if (t < BA_BLOCK - 1) v = v * sh[1][BA_BLOCK - 2 - t];    // product of the threads after t
-    __syncthreads();
-    return v;
-}
-
-// Scratch of the batched-affine path (global memory, [row][chunk] so that a warp's accesses are contiguous):
-//   pref  : (CHUNK/2 + 1) rows of field elements - prefix products per pair; the last row holds the running product
-//           before the chunk's first pair
-//   buf_a : CHUNK/2 rows of affine points (outputs of the even levels), buf_b : CHUNK/4 + 1 rows (odd levels)
-// `cap` chunks fit; chunks beyond it (only reachable with pathologically skewed scalars) take the XYZZ path.
-template <class F>
-struct BaScratch {
-    F* pref;
-    Affine<F>* buf_a;
-    Affine<F>* buf_b;
-    uint32_t cap;
-};
-static inline size_t ba_cap(size_t n_buckets, size_t max_chunks) { return std::min(max_chunks, n_buckets + n_buckets / 4 + 1024); }
-
-template <class F, int NLEV, int MINB>
-__global__ void __launch_bounds__(BA_BLOCK, MINB)
-ba_chunk_sum_kernel(const uint8_t* __restrict__ points, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ offsets,
-                    const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off, const uint32_t* __restrict__ work_bucket,
-                    uint32_t n_buckets, uint32_t CHUNK, uint8_t* partial, BaScratch<F> S) {
-    __shared__ F sh[2][BA_BLOCK];
-    __shared__ F ginv;
-    const uint32_t total = chunk_off[n_buckets];
-    const uint32_t per_iter = gridDim.x * BA_BLOCK;
-    const uint32_t iters = (total + per_iter - 1) / per_iter;      // uniform: every thread joins every block-wide scan
-    const size_t cap = S.cap;
-    F* const before_row = S.pref + (size_t)(CHUNK / 2) * cap;
-    // chunk of iteration `it`: index w, first entry, entry count (0 when the thread has no chunk / no scratch slot)
-    auto chunk_of = [&](uint32_t it, uint32_t& w, uint32_t& beg) -> uint32_t {
-        w = (it * gridDim.x + blockIdx.x) * BA_BLOCK + threadIdx.x;
-        beg = 0;
-        if (w >= total) return 0;
-        const uint32_t b = work_bucket[w];
-        const uint32_t ci = w - chunk_off[b];
-        beg = offsets[b] + ci * CHUNK;
-        return min(offsets[b] + hist[b], beg + CHUNK) - beg;
-    };
-#pragma unroll 1
-    for (int lev = 0; lev < NLEV; ++lev) {
-        const Affine<F>* const src_buf = (lev & 1) ? S.buf_a : S.buf_b;
-        Affine<F>* const dst_buf = (lev & 1) ? S.buf_b : S.buf_a;
-        F run = F::one();
-#pragma unroll 1
-        for (uint32_t it = 0; it < iters; ++it) {
-            uint32_t w, beg;
-            uint32_t n = chunk_of(it, w, beg);
-            if (w >= cap) n = 0;
-            for (int l = 0; l < lev; ++l) n = (n + 1) >> 1;
-            if (w < total && w < cap) run.store(before_row + w);
-            if (lev == 0) ba_phase_a(BaTableSource<F>{points, entries + beg}, (int)(n >> 1), S.pref + w, cap, run);
-            else ba_phase_a(BaBufferSource<F>{src_buf + w, cap}, (int)(n >> 1), S.pref + w, cap, run);
-        }
-        F v = block_batch_inverse(run, sh, &ginv);
-#pragma unroll 1
-        for (uint32_t it = iters; it-- > 0;) {
-            uint32_t w, beg;
-            uint32_t n = chunk_of(it, w, beg);
-            if (w >= cap) n = 0;
-            for (int l = 0; l < lev; ++l) n = (n + 1) >> 1;
-            if (n == 0) continue;
-            const int np = (int)(n >> 1);
-            const F before = F::load(before_row + w);
-            if (lev == 0) {
-                const BaTableSource<F> src{points, entries + beg};
-                ba_phase_b(src, np, S.pref + w, cap, before, v, dst_buf + w, cap);
-                if (n & 1) src.get((int)n - 1).store(dst_buf + (size_t)np * cap + w);
-            } else {
-                const BaBufferSource<F> src{src_buf + w, cap};
-                ba_phase_b(src, np, S.pref + w, cap, before, v, dst_buf + w, cap);
-                if (n & 1) src.get((int)n - 1).store(dst_buf + (size_t)np * cap + w);
-            }
-        }
-    }
-    const Affine<F>* const last_buf = (NLEV & 1) ? S.buf_a : S.buf_b;
-#pragma unroll 1
-    for (uint32_t it = 0; it < iters; ++it) {
-        uint32_t w, beg;
-        uint32_t n = chunk_of(it, w, beg);
-        if (w >= total) continue;
-        XYZZ<F> acc = XYZZ<F>::inf();
-        if (w >= cap) {
-            const BaTableSource<F> src{points, entries + beg};
-            for (uint32_t i = 0; i < n; ++i) acc.madd(src.get((int)i), false);
-        } else {
-            for (int l = 0; l < NLEV; ++l) n = (n + 1) >> 1;
-            const BaBufferSource<F> src{last_buf + w, cap};
-            Affine<F> nxt = src.get(0);
-            for (uint32_t i = 0; i < n; ++i) {        // one point ahead: the load overlaps the addition
-                const Affine<F> p = nxt;
-                if (i + 1 < n) nxt = src.get((int)i + 1);
-                acc.madd(p, false);
-            }
-        }
-        acc.store(partial + sizeof(XYZZ<F>) * (size_t)w);
-    }
-}
-
 // extra reduction pass: level `level` items of a bucket (XYZZ partial sums, contiguous at off_in[b]) are combined
 // PASS_FANIN at a time into level + 1 items at off_out[b]; spreads the partial sums of a heavy bucket (many equal
 // small scalars) over threads instead of leaving them to the running-sum thread
@@ -457,7 +327,8 @@ partial_pass_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__
 
 // one thread per GROUP consecutive buckets of one window: sum_b (b+1) B_b restricted to the group, as
 // T + first_index * S with T the in-group weighted sum and S the plain sum
-template <class F>
+// AFFINE: the items are affine points (outputs of the batched-affine sweeps) and are added with mixed additions
+template <class F, bool AFFINE>
 __global__ void __launch_bounds__(128)
 group_sum_kernel(const uint8_t* __restrict__ partial, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off,
                  uint32_t half, uint32_t n_groups_total, uint32_t CHUNK, uint32_t levels, uint32_t GROUP, uint8_t* group_out) {
@@ -470,7 +341,10 @@ group_sum_kernel(const uint8_t* __restrict__ partial, const uint32_t* __restrict
     for (uint32_t b = hi; b-- > lo;) {
         const uint32_t bucket = window * half + b;
         const uint32_t nch = scan_f(hist[bucket], CHUNK, levels);
-        for (uint32_t i = 0; i < nch; ++i) running.add(XYZZ<F>::load(partial + sizeof(XYZZ<F>) * (size_t)(chunk_off[bucket] + i)));
+        for (uint32_t i = 0; i < nch; ++i) {
+            if (AFFINE) running.madd(Affine<F>::load(partial + sizeof(Affine<F>) * (size_t)(chunk_off[bucket] + i)), false);
+            else running.add(XYZZ<F>::load(partial + sizeof(XYZZ<F>) * (size_t)(chunk_off[bucket] + i)));
+        }
         total.add(running);
     }
     // total = sum (b - lo + 1) B_b ; add lo * running  (lo < 2^15)
@@ -511,29 +385,65 @@ __global__ void gather_windows_kernel(const uint8_t* __restrict__ group_out, uin
     XYZZ<F>::load(group_out + sizeof(XYZZ<F>) * (size_t)j * groups_per_window).store(out + sizeof(XYZZ<F>) * (size_t)j);
 }
 
+// ---------------------------------------------------------------- streaming batched-affine path (msm_ba.cuh)
+// entries / hist / offsets: the counting-sorted digits.  Produces the per-group running sums in group_out.
+// The sweeps (forward, backward) saturate memory / the multiplier pipe and go to the lane's low-priority stream; the
+// tiny kernels of the grid-wide inversion stay on the high-priority one so that they slip between other lanes' blocks.
 template <class F>
-static void launch_ba(int levels, int waves, const uint8_t* points, const uint32_t* entries, const uint32_t* offsets, const uint32_t* hist,
-                      const uint32_t* chunk_off, const uint32_t* work_bucket, uint32_t n_buckets, uint32_t chunk, uint8_t* partial,
-                      uint8_t* scratch, size_t cap, cudaStream_t st) {
-    constexpr int MINB = 3;   // 168 registers: no spills in the pair loops (at 128 the compiler spills ~1 KB into them)
-    (void)waves;
-    const int grid = 148 * MINB;     // every thread walks all of its chunks between two block-wide inversions
-    BaScratch<F> S;
-    S.cap = (uint32_t)cap;
-    S.pref = reinterpret_cast<F*>(scratch);
-    S.buf_a = reinterpret_cast<Affine<F>*>(scratch + sizeof(F) * (chunk / 2 + 1) * cap);
-    S.buf_b = S.buf_a + (size_t)(chunk / 2) * cap;
-    if (levels >= 3) ba_chunk_sum_kernel<F, 3, MINB><<<grid, BA_BLOCK, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, chunk, partial, S);
-    else if (levels == 2) ba_chunk_sum_kernel<F, 2, MINB><<<grid, BA_BLOCK, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, chunk, partial, S);
-    else ba_chunk_sum_kernel<F, 1, MINB><<<grid, BA_BLOCK, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, chunk, partial, S);
+static void run_ba(const MsmConfig& cfg, const uint8_t* points, const uint32_t* entries, const uint32_t* hist, const uint32_t* offsets,
+                   uint32_t n_buckets, size_t max_entries, uint32_t* tiles, uint8_t* ws, const Digits& D, uint32_t groups, uint8_t* group_out,
+                   cudaStream_t st, cudaEvent_t* ev, const typename MsmPlan<F>::Heavy* heavy) {
+    const int L = cfg.ba_levels;
+    const size_t s1 = BaPlan<F>::slots_bound(max_entries, n_buckets, 1), s2 = BaPlan<F>::slots_bound(max_entries, n_buckets, 2);
+    const size_t t1 = (s1 + BA_K - 1) / BA_K;
+    uint8_t* p = ws;
+    auto take = [&](size_t x) { uint8_t* r = p; p += (x + 255) & ~(size_t)255; return r; };
+    F* stage = (F*)take(4 * sizeof(F) * s1);
+    F* prefix = (F*)take(sizeof(F) * s1);
+    Affine<F>* ping = (Affine<F>*)take(sizeof(Affine<F>) * s1);
+    Affine<F>* pong = (Affine<F>*)take(sizeof(Affine<F>) * s2);
+    uint32_t* slot_bucket = (uint32_t*)take(4 * s1);
+    F* tot = (F*)take(sizeof(F) * t1);
+    F* binv_scratch = (F*)take(sizeof(F) * binv_scratch_elems(t1));
+    const uint32_t* off[8];
+    off[0] = offsets;
+    for (int l = 1; l <= L; ++l) {
+        uint32_t* o = (uint32_t*)take(4 * ((size_t)n_buckets + 1));
+        exclusive_scan(hist, n_buckets, 1u << l, 0, o, tiles, st);     // scan of ceil(size / 2^l)
+        off[l] = o;
+    }
+    cudaStream_t hv = (heavy && heavy->st != st) ? heavy->st : st;
+    auto to_heavy = [&]() { if (hv != st) { cudaEventRecord(heavy->before, st); cudaStreamWaitEvent(hv, heavy->before, 0); } };
+    auto to_light = [&]() { if (hv != st) { cudaEventRecord(heavy->after, hv); cudaStreamWaitEvent(st, heavy->after, 0); } };
+    const Affine<F>* in = nullptr;
+    Affine<F>* out = ping;
+    for (int l = 0; l < L; ++l) {
+        const size_t slots = BaPlan<F>::slots_bound(max_entries, n_buckets, l + 1);
+        const uint32_t n_threads = (uint32_t)((slots + BA_K - 1) / BA_K);
+        const uint32_t blocks = (n_threads + BA_THREADS - 1) / BA_THREADS;
+        fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, off[l + 1], n_buckets, 1u << (l + 1), 0, slot_bucket);
+        BaLevel lv{hist, off[l], off[l + 1], slot_bucket, n_buckets, (uint32_t)l};
+        to_heavy();
+        if (ev && l == 0) cudaEventRecord(ev[0], hv);
+        if (l == 0) ba_forward_kernel<F, true><<<blocks, BA_THREADS, 0, hv>>>(lv, points, entries, nullptr, stage, prefix, tot, n_threads);
+        else ba_forward_kernel<F, false><<<blocks, BA_THREADS, 0, hv>>>(lv, nullptr, nullptr, in, nullptr, prefix, tot, n_threads);
+        to_light();
+        batch_inverse<F>(tot, n_threads, binv_scratch, st);
+        to_heavy();
+        if (l == 0) ba_backward_kernel<F, true><<<blocks, BA_THREADS, 0, hv>>>(lv, nullptr, stage, prefix, tot, out, n_threads);
+        else ba_backward_kernel<F, false><<<blocks, BA_THREADS, 0, hv>>>(lv, in, nullptr, prefix, tot, out, n_threads);
+        if (ev && l == L - 1) cudaEventRecord(ev[1], hv);
+        to_light();
+        ZKE_COUNT_LAUNCH(3);
+        in = out;
+        out = (out == ping) ? pong : ping;
+    }
+    group_sum_kernel<F, true><<<(groups + 127) / 128, 128, 0, st>>>((const uint8_t*)in, hist, off[L], D.half, groups, 1u << L, 0, D.group, group_out);
+    ZKE_COUNT_LAUNCH(1);
 }
 template <>
-void launch_ba<Fq2>(int, int, const uint8_t*, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, uint32_t, uint8_t*,
-                    uint8_t*, size_t, cudaStream_t) {}
-template <class F>
-static size_t ba_scratch_bytes(size_t chunk, size_t cap) {
-    return sizeof(F) * (chunk / 2 + 1) * cap + 2 * sizeof(F) * ((chunk / 2) + (chunk / 4 + 1)) * cap;
-}
+void run_ba<Fq2>(const MsmConfig&, const uint8_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, size_t, uint32_t*, uint8_t*, const Digits&,
+                 uint32_t, uint8_t*, cudaStream_t, cudaEvent_t*, const MsmPlan<Fq2>::Heavy*) {}
 
 // ---------------------------------------------------------------- host orchestration
 #if defined(ZKE_MSM_G1)
@@ -549,13 +459,12 @@ MsmConfig msm_config_full(uint32_t n, bool precomputed) {
     c.c = n >= (1u << 18) ? 16 : (n >= (1u << 12) ? 12 : 8);
     c.chunk = 256; c.group = n >= (1u << 20) ? 64 : 16; c.classify = false; c.extra_passes = 0;   // group 64: 46.2 vs 45.8 proofs/s at 2^22
     c.precomputed = precomputed;
-    // Batched-affine bucket accumulation (ba.cuh) is an opt-in experiment: ZKE_H_BA=<levels> at key-setup time.
-    // Measured on B200 at 2^22 points: 11.2 ms (2 levels) against 10.9 ms for the XYZZ kernel - it executes 15 % fewer
-    // instructions but waits on its scratch traffic (27 GB of DRAM reads/writes, fmaheavy pipe 60 % busy instead of
-    // 86 %), see profiles/ncu_r01_ba_summary.txt.
-    if (const char* e = getenv("ZKE_H_BA")) c.ba_levels = precomputed ? std::max(0, std::min(3, atoi(e))) : 0;
+    // Streaming batched-affine bucket accumulation (msm_ba.cuh): the first `ba_levels` levels of every bucket's addition
+    // tree in affine coordinates (6 products per addition instead of 10).  ZKE_H_BA=<levels> at key-setup time
+    // (0 = the XYZZ bucket kernel of round 1).
+    c.ba_levels = (precomputed && n >= (1u << 12)) ? 4 : 0;
+    if (const char* e = getenv("ZKE_H_BA")) c.ba_levels = precomputed ? std::max(0, std::min(6, atoi(e))) : 0;
     if (const char* e = getenv("ZKE_H_GROUP")) c.group = (uint32_t)std::max(2, atoi(e));   // experiments
-    if (c.ba_levels) c.chunk = 160;   // one chunk per bucket at the expected ~104 entries; sizes the batched-affine scratch rows
     if (precomputed) {
         // one shared bucket set of 2^(c-1) buckets: pick c so that the buckets (~ n * W / 2^(c-1) entries each) still
         // number in the hundreds of thousands for parallelism; 13 table levels at 2^22 points (3.5 GB)
@@ -591,7 +500,7 @@ size_t MsmPlan<F>::workspace_bytes(uint32_t n, const MsmConfig& cfg) {
     al(4 * (n_buckets + 1));           // second offsets array
     al(sizeof(XYZZ<F>) * groups);      // group sums
     al(sizeof(XYZZ<F>) * ((size_t)n / LIST_FANIN + 2) * 2);  // list reduction ping-pong
-    if (cfg.ba_levels > 0 && sizeof(F) == 32) al(ba_scratch_bytes<F>(cfg.chunk, ba_cap(n_buckets, max_chunks)));
+    if (cfg.ba_levels > 0 && sizeof(F) == 32) al(BaPlan<F>::bytes(max_entries, n_buckets, cfg.ba_levels));
     const size_t order_cells = ((max_chunks + ORDER_BLOCK - 1) / ORDER_BLOCK) * cfg.chunk;
     al(4 * max_chunks);                       // order
     al(4 * (order_cells + 1));                // per-block size histograms, bin-major
@@ -637,7 +546,8 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     const size_t list_slots = (size_t)n / LIST_FANIN + 2;
     uint8_t* red_a = take(sizeof(XYZZ<F>) * list_slots);
     uint8_t* red_b = take(sizeof(XYZZ<F>) * list_slots);
-    uint8_t* ba_scratch = (cfg.ba_levels > 0 && sizeof(F) == 32) ? take(ba_scratch_bytes<F>(cfg.chunk, ba_cap(n_buckets, max_chunks))) : nullptr;
+    const bool use_ba = cfg.ba_levels > 0 && sizeof(F) == 32;      // G1 only
+    uint8_t* ba_ws = use_ba ? take(BaPlan<F>::bytes(max_entries, n_buckets, cfg.ba_levels)) : nullptr;
     const size_t order_cells = ((max_chunks + ORDER_BLOCK - 1) / ORDER_BLOCK) * cfg.chunk;
     uint32_t* order = (uint32_t*)take(4 * max_chunks);
     uint32_t* order_mat = (uint32_t*)take(4 * (order_cells + 1));
@@ -682,57 +592,56 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     digit_hist_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, hist);
     exclusive_scan(hist, n_buckets, 0, 0, offsets, tiles, st);
     digit_scatter_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, offsets, cursor, entries);
-    exclusive_scan(hist, n_buckets, D.chunk, 0, chunk_off, tiles, st);
-    fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, chunk_off, n_buckets, D.chunk, 0, work_bucket);
-    {   // order[] = chunks sorted by size, largest first
-        const uint32_t nblk = (uint32_t)((max_chunks + ORDER_BLOCK - 1) / ORDER_BLOCK);
-        chunk_key_hist_kernel<<<nblk, ORDER_BLOCK, 4 * D.chunk, st>>>(hist, chunk_off, work_bucket, n_buckets, D.chunk, order_mat);
-        exclusive_scan(order_mat, nblk * D.chunk, 0, 0, order_off, order_tiles, st);
-        chunk_order_kernel<<<nblk, ORDER_BLOCK, 0, st>>>(hist, chunk_off, work_bucket, n_buckets, D.chunk, order_off, order);
-        ZKE_COUNT_LAUNCH(2);
+    if (use_ba) {
+        run_ba<F>(cfg, points, entries, hist, offsets, n_buckets, max_entries, tiles, ba_ws, D, groups, group_out, st, ev, heavy);
+    } else {
+        exclusive_scan(hist, n_buckets, D.chunk, 0, chunk_off, tiles, st);
+        fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, chunk_off, n_buckets, D.chunk, 0, work_bucket);
+        {   // order[] = chunks sorted by size, largest first
+            const uint32_t nblk = (uint32_t)((max_chunks + ORDER_BLOCK - 1) / ORDER_BLOCK);
+            chunk_key_hist_kernel<<<nblk, ORDER_BLOCK, 4 * D.chunk, st>>>(hist, chunk_off, work_bucket, n_buckets, D.chunk, order_mat);
+            exclusive_scan(order_mat, nblk * D.chunk, 0, 0, order_off, order_tiles, st);
+            chunk_order_kernel<<<nblk, ORDER_BLOCK, 0, st>>>(hist, chunk_off, work_bucket, n_buckets, D.chunk, order_off, order);
+            ZKE_COUNT_LAUNCH(2);
+        }
+        cudaStream_t st_light = st;
+        if (heavy && heavy->st != st) {
+            cudaEventRecord(heavy->before, st);
+            cudaStreamWaitEvent(heavy->st, heavy->before, 0);
+            st = heavy->st;
+        }
+        if (ev) cudaEventRecord(ev[0], st);
+        {
+            // blocks per SM the bucket kernel is compiled for (register cap 128 / 96 / 80): more resident warps hide the
+            // IMAD.WIDE carry-chain latency; tunable for experiments with ZKE_CHUNK_MINB
+            int minb = sizeof(F) == 32 ? 5 : 4, waves = 4;
+            if (const char* e = getenv("ZKE_CHUNK_MINB")) minb = atoi(e);
+            if (const char* e = getenv("ZKE_CHUNK_WAVES")) waves = std::max(1, atoi(e));
+            if (minb >= 6) chunk_sum_kernel<F, 6><<<148 * 6 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
+            else if (minb == 5) chunk_sum_kernel<F, 5><<<148 * 5 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
+            else chunk_sum_kernel<F, 4><<<148 * 4 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
+        }
+        if (ev) cudaEventRecord(ev[1], st);
+        if (st != st_light) {
+            cudaEventRecord(heavy->after, st);
+            cudaStreamWaitEvent(st_light, heavy->after, 0);
+            st = st_light;
+        }
+        // extra passes over the per-chunk partial sums
+        uint8_t *items = partial, *items_next = partial2;
+        uint32_t *off_cur = chunk_off, *off_next = off2;
+        uint32_t levels = 0;
+        for (uint32_t pass = 0; pass < cfg.extra_passes; ++pass) {
+            exclusive_scan(hist, n_buckets, D.chunk, levels + 1, off_next, tiles, st);
+            fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, off_next, n_buckets, D.chunk, levels + 1, work_bucket);
+            partial_pass_kernel<F><<<148 * 4, 128, 0, st>>>(items, hist, off_cur, off_next, work_bucket, n_buckets, D.chunk, levels, items_next);
+            ZKE_COUNT_LAUNCH(2);
+            uint8_t* t = items; items = items_next; items_next = t;
+            uint32_t* o = off_cur; off_cur = off_next; off_next = o;
+            ++levels;
+        }
+        group_sum_kernel<F, false><<<(groups + 127) / 128, 128, 0, st>>>(items, hist, off_cur, D.half, groups, D.chunk, levels, D.group, group_out);
     }
-    cudaStream_t st_light = st;
-    if (heavy && heavy->st != st) {
-        cudaEventRecord(heavy->before, st);
-        cudaStreamWaitEvent(heavy->st, heavy->before, 0);
-        st = heavy->st;
-    }
-    if (ev) cudaEventRecord(ev[0], st);
-    {
-        // blocks per SM the bucket kernel is compiled for (register cap 128 / 96 / 80): more resident warps hide the
-        // IMAD.WIDE carry-chain latency; tunable for experiments with ZKE_CHUNK_MINB
-        int minb = sizeof(F) == 32 ? 5 : 4, waves = 4;
-        if (const char* e = getenv("ZKE_CHUNK_MINB")) minb = atoi(e);
-        if (const char* e = getenv("ZKE_CHUNK_WAVES")) waves = std::max(1, atoi(e));
-        int ba_levels = cfg.ba_levels;
-        if (const char* e = getenv("ZKE_BA_LEVELS")) { if (cfg.ba_levels > 0) ba_levels = atoi(e); }
-        if (cfg.ba_levels <= 0 || (D.chunk & 3) || sizeof(F) != 32) ba_levels = 0;   // scratch is only planned for ba_levels > 0; G1 only
-        if (ba_levels > 0) launch_ba<F>(ba_levels, waves, points, entries, offsets, hist, chunk_off, work_bucket, n_buckets, D.chunk, partial,
-                                        ba_scratch, ba_cap(n_buckets, max_chunks), st);
-        else if (minb >= 6) chunk_sum_kernel<F, 6><<<148 * 6 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
-        else if (minb == 5) chunk_sum_kernel<F, 5><<<148 * 5 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
-        else chunk_sum_kernel<F, 4><<<148 * 4 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
-    }
-    if (ev) cudaEventRecord(ev[1], st);
-    if (st != st_light) {
-        cudaEventRecord(heavy->after, st);
-        cudaStreamWaitEvent(st_light, heavy->after, 0);
-        st = st_light;
-    }
-    // extra passes over the per-chunk partial sums
-    uint8_t *items = partial, *items_next = partial2;
-    uint32_t *off_cur = chunk_off, *off_next = off2;
-    uint32_t levels = 0;
-    for (uint32_t pass = 0; pass < cfg.extra_passes; ++pass) {
-        exclusive_scan(hist, n_buckets, D.chunk, levels + 1, off_next, tiles, st);
-        fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, off_next, n_buckets, D.chunk, levels + 1, work_bucket);
-        partial_pass_kernel<F><<<148 * 4, 128, 0, st>>>(items, hist, off_cur, off_next, work_bucket, n_buckets, D.chunk, levels, items_next);
-        ZKE_COUNT_LAUNCH(2);
-        uint8_t* t = items; items = items_next; items_next = t;
-        uint32_t* o = off_cur; off_cur = off_next; off_next = o;
-        ++levels;
-    }
-    group_sum_kernel<F><<<(groups + 127) / 128, 128, 0, st>>>(items, hist, off_cur, D.half, groups, D.chunk, levels, D.group, group_out);
     window_reduce_kernel<F><<<bucket_sets, 512, 0, st>>>(group_out, groups_per_window);
     gather_windows_kernel<F><<<1, 64, 0, st>>>(group_out, groups_per_window, bucket_sets, res_windows);
     ZKE_COUNT_LAUNCH(7);

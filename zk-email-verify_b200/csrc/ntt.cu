@@ -4,7 +4,9 @@
 // (algorithmic bytes per transform: 2 * 32 * N).  The inverse transform is decimation-in-frequency
 // (natural in, bit-reversed out) and the forward transform decimation-in-time (bit-reversed in, natural out), so
 // no bit-reversal permutation is ever materialised; the coset shift g^j / N is fused into the store of the last
-// inverse pass.  Twiddles are 32-byte vector loads from a table of N/2 powers that stays L2-resident (64 MB at 2^22).
+// inverse pass.  Twiddles (and the coset factors) are constants: the tables hold them as fixed-operand pairs
+// {w in standard form, floor(w 2^256 / r)} (64 bytes) and every butterfly product is Fp::mul_shoup (ff.cuh) - 99
+// IMAD.WIDE + 16 IMAD instead of the 136 IMAD.WIDE of a Montgomery product; the data stays in Montgomery form.
 #include "device_engine.cuh"
 #include "ntt.cuh"
 
@@ -64,13 +66,13 @@ ntt_pass_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, cons
         const int e0 = sidx(j0, l), e1 = sidx(j0 + h, l);
         const uint32_t idx0 = gidx(j0, l);
         const uint32_t tw_i = (idx0 & ((1u << st) - 1)) << (log_n - 1 - st);
-        const Fr w = Fr::load(tw + 32ull * tw_i);
+        const Fr w = Fr::load(tw + 64ull * tw_i), wq = Fr::load(tw + 64ull * tw_i + 32);
         Fr u = S.get(e0), v = S.get(e1);
         if (DIF) {
             S.put(e0, u + v);
-            S.put(e1, (u - v) * w);
+            S.put(e1, Fr::mul_shoup(u - v, w.v, wq.v));
         } else {
-            Fr x = v * w;
+            Fr x = Fr::mul_shoup(v, w.v, wq.v);
             S.put(e0, u + x);
             S.put(e1, u - x);
         }
@@ -81,7 +83,7 @@ ntt_pass_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, cons
         if (strided) { l2 = e % L; j = e / L; } else { j = e % J; l2 = e / J; }
         const uint32_t g = gidx(j, l2);
         Fr x = S.get(e);
-        if (scale) x = x * Fr::load(scale + 32ull * g);
+        if (scale) { const Fr sc = Fr::load(scale + 64ull * g), scq = Fr::load(scale + 64ull * g + 32); x = Fr::mul_shoup(x, sc.v, scq.v); }
         x.store(data + 32ull * g);
     }
 }
@@ -92,7 +94,7 @@ ntt_pass_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, cons
 // arithmetic is shifts and masks; the twiddle of the next stage is fetched before the current stage's product so
 // the L2 latency of the table lookup overlaps the multiplication.
 template <bool DIF, int K, bool STRIDED>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 ntt_pass_fast_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, const uint8_t* __restrict__ scale,
                      int log_n, int s_lo_arg) {
     const int s_lo = STRIDED ? s_lo_arg : 0;   // the contiguous pass always starts at stage 0 (compile-time stages)
@@ -137,24 +139,28 @@ ntt_pass_fast_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw,
     };
     auto tw_ptr = [&](int st, uint32_t j0) {
         const uint32_t idx0 = gidx(j0, l);
-        return tw + 32ull * ((idx0 & ((1u << st) - 1)) << (log_n - 1 - st));
+        return tw + 64ull * ((idx0 & ((1u << st) - 1)) << (log_n - 1 - st));
     };
-    Fr w_next = Fr::load(tw_ptr(stage_of(0), j0_of(stage_of(0))));
+    const uint8_t* twp = tw_ptr(stage_of(0), j0_of(stage_of(0)));
+    Fr w_next = Fr::load(twp), wq_next = Fr::load(twp + 32);
     __syncthreads();
 #pragma unroll
     for (int step = 0; step < K; ++step) {
         const int st = stage_of(step);
         const uint32_t j0 = j0_of(st);
         const uint32_t e0 = sidx(j0, l), e1 = sidx(j0 + (1u << (st - s_lo)), l);
-        const Fr w = w_next;
-        if (step + 1 < K) w_next = Fr::load(tw_ptr(stage_of(step + 1), j0_of(stage_of(step + 1))));
+        const Fr w = w_next, wq = wq_next;
+        if (step + 1 < K) {
+            twp = tw_ptr(stage_of(step + 1), j0_of(stage_of(step + 1)));
+            w_next = Fr::load(twp); wq_next = Fr::load(twp + 32);
+        }
         const Fr u = sget(e0), v = sget(e1);
         const bool trivial = !STRIDED && st == 0;   // stage 0: every twiddle is omega^0 = 1, no product
         if (DIF) {
             sput(e0, u + v);
-            sput(e1, trivial ? (u - v) : (u - v) * w);
+            sput(e1, trivial ? (u - v) : Fr::mul_shoup(u - v, w.v, wq.v));
         } else {
-            const Fr x = trivial ? v : v * w;
+            const Fr x = trivial ? v : Fr::mul_shoup(v, w.v, wq.v);
             sput(e0, u + x);
             sput(e1, u - x);
         }
@@ -166,8 +172,8 @@ ntt_pass_fast_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw,
         const uint32_t j = STRIDED ? (e >> L_LOG) : (e & (J - 1)), l2 = STRIDED ? (e & (L - 1)) : (e >> K);
         const uint32_t g = gidx(j, l2);
         if (scale) {
-            Fr x = sget(e) * Fr::load(scale + 32ull * g);
-            x.store(data + 32ull * g);
+            const Fr sc = Fr::load(scale + 64ull * g), scq = Fr::load(scale + 64ull * g + 32);
+            Fr::mul_shoup(sget(e), sc.v, scq.v).store(data + 32ull * g);
         } else {
             uint4* dst = reinterpret_cast<uint4*>(data + 32ull * g);
             dst[0] = plane0[e];

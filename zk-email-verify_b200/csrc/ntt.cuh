@@ -6,13 +6,14 @@ namespace zke {
 namespace dev {
 
 struct NttTables {
-    const uint8_t* tw_fwd;   // [N/2][32] omega^k, Montgomery
-    const uint8_t* tw_inv;   // [N/2][32] omega^-k
+    const uint8_t* tw_fwd;   // [N/2][2][32] omega^k as a fixed-operand pair {w (standard form), floor(w 2^256 / r)}
+    const uint8_t* tw_inv;   // [N/2][2][32] omega^-k
     int log_n;
 };
 
 // In-place inverse transform, natural order in, BIT-REVERSED order out, not scaled by 1/N.  If scale_bitrev is
-// non-null, output position p is multiplied by scale_bitrev[p] (used to fuse the coset shift g^j / N).
+// non-null, output position p is multiplied by scale_bitrev[p] (used to fuse the coset shift g^j / N); the scale table
+// holds fixed-operand pairs like the twiddle tables ([N][2][32]).
 void launch_intt_dif(uint8_t* data, const NttTables& T, const uint8_t* scale_bitrev, cudaStream_t st);
 // In-place forward transform, bit-reversed order in, natural order out.
 void launch_ntt_dit(uint8_t* data, const NttTables& T, cudaStream_t st);
