@@ -13,3 +13,4 @@ from .engine import AssertFailed, Context, Zkey, device_count, proof_to_json, ve
 from .chunked_zkey import generate_proof, verify_proof, register_circuit, generateProof, verifyProof  # noqa: F401
 from . import synthetic  # noqa: F401,E402
 from . import iden3_binfile  # noqa: F401,E402
+from . import verifier_args  # noqa: F401,E402

@@ -4,9 +4,11 @@ Mirrors `verifyDKIMSignature` (/root/reference/packages/helpers/src/dkim/index.t
 modified mailauth it drives: message splitting (lib/mailauth/message-parser.ts:43-113), signed-header selection
 bottom-up per h= (lib/mailauth/tools.ts:107-140), relaxed header canonicalisation (tools.ts:441-454,
 header/relaxed.ts:5-81 incl. emptying b=), relaxed / simple body canonicalisation (body/relaxed.ts:157-273,
-body/simple.ts:59-106).  Differences by design: key lookup goes through a caller-supplied `resolver`
-(the reference does DNS-over-HTTPS, dkim/dns-over-http.ts:100-156 - no network here) and the email sanitizers
-(dkim/sanitizers.ts) are not applied.  CPU-side I/O and string work; not part of the GPU hot path.
+body/simple.ts:59-106), plus the sanitizer retry loop (dkim/index.ts:49-66 with dkim/sanitizers.ts:1-67: when the first
+attempt ends in "bad signature" every sanitizer is tried and the first passing one is reported as
+`appliedSanitization`).  Difference by design: key lookup goes through a caller-supplied `resolver` (the reference does
+DNS-over-HTTPS with an archive fallback, dkim/dns-over-http.ts:100-156, dkim/index.ts:105-131 - no network here); all
+records the resolver returns are tried in turn.  CPU-side I/O and string work; not part of the GPU hot path.
 """
 from __future__ import annotations
 import base64
@@ -132,12 +134,54 @@ def _offline_resolver(name, rtype):
     raise LookupError("No DNS records found from any source")
 
 
-def verify_dkim_signature(email: bytes | str, domain: str = "", enable_sanitization: bool = True,
-                          fallback_to_zk_email_dns_archive: bool = False, skip_body_hash: bool = False,
-                          resolver=None) -> DKIMVerificationResult:
-    """verifyDKIMSignature (dkim/index.ts:36-97).  `resolver(name, "TXT") -> list[str]` supplies DKIM key records."""
-    raw = email.encode("latin-1") if isinstance(email, str) else bytes(email)
-    resolver = resolver or _offline_resolver
+# ---- dkim/sanitizers.ts:1-67 -------------------------------------------------------------------------------------
+def _get_header_value(email: str, header: str) -> str:
+    start = email.find(f"{header}: ")
+    if start < 0:
+        return ""
+    start += len(header) + 2
+    end = email.find("\n", start)
+    return email[start:end if end >= 0 else len(email)]
+
+
+def _set_header_value(email: str, header: str, value: str) -> str:
+    old = _get_header_value(email, header)
+    return email.replace(old, value, 1) if old else email
+
+
+def revertGoogleMessageId(email: str) -> str:   # sanitizers.ts:16-29
+    """Google replaces Message-ID when it ARC-forwards and keeps the original in X-Google-Original-Message-ID."""
+    if "ARC-Authentication-Results" not in email:
+        return email
+    original = _get_header_value(email, "X-Google-Original-Message-ID")
+    if original:
+        return _set_header_value(email, "Message-ID", original)
+    return email
+
+
+def removeLabels(email: str) -> str:            # sanitizers.ts:32-36
+    """`Subject: [ListName] Newsletter` -> `Subject: Newsletter` (the JS regex is greedy, so is this one)."""
+    return re.sub(r"Subject: \[.*\]", "Subject:", email, count=1)
+
+
+def insert13Before10(email: str) -> str:        # sanitizers.ts:40-57
+    return re.sub(r"(?<!\r)\n", "\r\n", email)
+
+
+def sanitizeTabs(email: str) -> str:            # sanitizers.ts:61-63 (first occurrence only, as String.replace does)
+    return email.replace("=09", "\t", 1)
+
+
+sanitizers = [revertGoogleMessageId, removeLabels, insert13Before10, sanitizeTabs]   # sanitizers.ts:65
+
+
+class _Attempt:
+    def __init__(self, result=None, comment=None, domain="", found=False):
+        self.result, self.comment, self.domain, self.found = result, comment, domain, found
+
+
+def _try_verify_dkim(raw: bytes, domain: str, skip_body_hash: bool, resolver) -> _Attempt:
+    """tryVerifyDKIM (dkim/index.ts:99-158): the result for `domain` (default: the From domain)."""
     parsed, body = split_message(raw)
     if not domain:
         froms = [h for k, h in parsed if k == "from"]
@@ -170,14 +214,19 @@ def verify_dkim_signature(email: bytes | str, domain: str = "", enable_sanitizat
             last_reason = "body hash did not verify"
             continue
         headers = signed_header_bytes(parsed, line, tags.get("h", ""), hc)
-        signature = base64.b64decode(re.sub(r"\s+", "", tags.get("b", "")))
+        try:
+            signature = base64.b64decode(re.sub(r"\s+", "", tags.get("b", "")))
+        except Exception:
+            last_reason = "bad signature"
+            continue
         selector = tags.get("s", "")
         try:
             records = resolver(f"{selector}._domainkey.{domain}", "TXT")
-        except Exception as e:  # dkim/index.ts:105-131
-            last_reason = f"DNS failure: {e}"
+        except Exception:  # dkim/index.ts:105-131: no record from any source
+            last_reason = "no key"
             continue
-        for rec in records:
+        tried = False
+        for rec in records:     # every key the resolver knows for this selector is tried (DNS + archive keys, :120-129)
             ktags = parse_tag_list(rec)
             if "p" not in ktags or not ktags["p"]:
                 continue
@@ -187,16 +236,39 @@ def verify_dkim_signature(email: bytes | str, domain: str = "", enable_sanitizat
                 continue
             if not isinstance(pub, rsa.RSAPublicKey):
                 continue
+            tried = True
             try:
                 pub.verify(signature, headers, padding.PKCS1v15(), hashes.SHA256())
             except InvalidSignature:
                 last_reason = "bad signature"
                 continue
-            return DKIMVerificationResult(
+            return _Attempt(DKIMVerificationResult(
                 publicKey=pub.public_numbers().n, signature=int.from_bytes(signature, "big"), headers=headers,
                 body=canon_body, bodyHash=bh_tag, signingDomain=domain, selector=selector, algo=algo,
-                format=canon, modulusLength=pub.key_size)
-        last_reason = last_reason or "no key"
-    if not found:
-        raise ValueError(f"DKIM signature not found for domain {domain}")
-    raise ValueError(f"DKIM signature verification failed for domain {domain}. Reason: {last_reason}")
+                format=canon, modulusLength=pub.key_size), None, domain, True)
+        if not tried:
+            last_reason = last_reason or "no key"
+    return _Attempt(None, last_reason, domain, found)
+
+
+def verify_dkim_signature(email: bytes | str, domain: str = "", enable_sanitization: bool = True,
+                          fallback_to_zk_email_dns_archive: bool = False, skip_body_hash: bool = False,
+                          resolver=None) -> DKIMVerificationResult:
+    """verifyDKIMSignature (dkim/index.ts:36-97).  `resolver(name, "TXT") -> list[str]` supplies DKIM key records."""
+    raw = email.encode("latin-1") if isinstance(email, str) else bytes(email)
+    resolver = resolver or _offline_resolver
+    att = _try_verify_dkim(raw, domain, skip_body_hash, resolver)
+    if not att.found:
+        raise ValueError(f"DKIM signature not found for domain {att.domain}")
+    applied = None
+    if att.result is None and att.comment == "bad signature" and enable_sanitization:      # index.ts:49-66
+        text = raw.decode("latin-1")
+        for sanitize in sanitizers:
+            retry = _try_verify_dkim(sanitize(text).encode("latin-1"), domain, skip_body_hash, resolver)
+            if retry.result is not None:
+                att, applied = retry, sanitize.__name__
+                break
+    if att.result is None:
+        raise ValueError(f"DKIM signature verification failed for domain {att.domain}. Reason: {att.comment}")
+    att.result.appliedSanitization = applied
+    return att.result
