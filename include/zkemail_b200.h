@@ -189,6 +189,34 @@ int zke_wtns_prove(zke_ctx* x, const void* wtns_bytes, size_t len, const uint8_t
                    char* err, size_t errcap);
 
 /* ---------------------------------------------------------------------------------------------------
+ * One proof across 2, 4 or 8 GPUs (BASELINE configs[3] "sharded MSM", configs[4] "NCCL-sharded MSM+NTT").
+ * Every GPU (one process each) opens a context with the key and loads the same witness (zke_witness / zke_load_witness,
+ * batch 1); then, in lock step:
+ *     zke_shard_begin   mat-vec for the rows of this GPU's column range + the cross-block inverse NTT stages
+ *     [exchange 1]      all-to-all "columns -> rows" on the three vectors of zke_shard_vector (caller: NCCL / torch.distributed)
+ *     zke_shard_mid     block-local inverse stages, coset shift, block-local forward stages on this GPU's row block
+ *     [exchange 2]      all-to-all "rows -> columns"
+ *     zke_shard_end     cross-block forward stages, a o b - c on the column range (this GPU's H scalars), the five
+ *                       multi-exponentiations over this GPU's share of the points -> ZKE_SHARD_PARTIAL_BYTES
+ *     [all-gather]      of the partial blocks
+ *     zke_shard_combine (host only) adds the partial points and assembles the proof: bit-identical to the 1-GPU proof.
+ * Layout of the vectors: element i of the N = 2^domain_log2 evaluation vector at byte offset 32 i; block g = elements
+ * [g M, (g + 1) M) with M = N / world; GPU r owns row block r and the columns [r M / world, (r + 1) M / world) of
+ * every block.  Exchange 1 sends (block g, columns of r) to GPU g; exchange 2 is its inverse.
+ * ------------------------------------------------------------------------------------------------- */
+#define ZKE_SHARD_PARTIAL_BYTES 388   /* A, B1, C, H (G1: x, y) + B2 (G2: x.c0, x.c1, y.c0, y.c1), standard form LE, + u32 first bad row */
+int zke_shard_begin(zke_ctx* x, int rank, int world, char* err, size_t errcap);
+void* zke_shard_vector(zke_ctx* x, int which /* 0 a, 1 b, 2 c */, size_t* n_elems);   /* device pointer, 32 bytes per element */
+int zke_shard_mid(zke_ctx* x, char* err, size_t errcap);
+int zke_shard_end(zke_ctx* x, uint8_t* partial_out, uint8_t* publics_out, char* err, size_t errcap);
+int zke_shard_combine(const zke_zkey* z, const uint8_t* partials, int world, const uint8_t* rs, uint8_t* proof_out, int32_t* status,
+                      char* err, size_t errcap);
+/* the same with the five key points it needs given directly: alpha_1, beta_1, delta_1 (64 bytes each), beta_2, delta_2
+ * (128 bytes each), standard form LE - no GPU-resident key required (a coordinator process can combine) */
+int zke_shard_combine_raw(const uint8_t* key_points, const uint8_t* partials, int world, const uint8_t* rs, uint8_t* proof_out,
+                          int32_t* status, char* err, size_t errcap);
+
+/* ---------------------------------------------------------------------------------------------------
  * JSON faces of the boundary (snarkjs file formats; shapes as in
  * /root/reference/packages/rust-verifier/tests/data/proof_of_twitter/{vkey,proof,public}.json).
  * String outputs: pass the buffer capacity in *len; on return *len = bytes needed incl. NUL (rc -2 if too small).

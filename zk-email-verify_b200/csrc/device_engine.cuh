@@ -58,7 +58,11 @@ void launch_witness(const DevProgram& P, uint8_t* w_all, size_t stride_elems, co
 // flag[0] = 1 if any of the n 32-byte values is >= r, flag[1] = 1 if some witness (stride_elems apart) has w[0] != 1
 void launch_check_witness(const uint8_t* w_all, size_t stride_elems, uint32_t n_vars, uint32_t batch, uint32_t* flag, cudaStream_t st);
 
-void launch_build_ab(const DevR1cs& R, const uint8_t* w, uint8_t* a_out, uint8_t* b_out, uint8_t* c_out, uint32_t n, uint32_t* first_bad, cudaStream_t st);
+// map (optional): thread t handles row ((t >> log_cols) << log_m) + col0 + (t & (2^log_cols - 1)) instead of row t - the
+// rows of the column range one GPU holds when a proof is sharded (n = number of threads = rows handled).
+struct RowMap { int log_cols = -1, log_m = 0; uint32_t col0 = 0; };
+void launch_build_ab(const DevR1cs& R, const uint8_t* w, uint8_t* a_out, uint8_t* b_out, uint8_t* c_out, uint32_t n, uint32_t* first_bad, cudaStream_t st,
+                     const RowMap* map = nullptr);
 
 }  // namespace dev
 }  // namespace zke

@@ -189,6 +189,8 @@ struct zke_ctx {
     };
     Slot slots[2];
     uint64_t n_submitted = 0, n_collected = 0;
+    // intra-proof sharding (zke_shard_*): this GPU's place among `shard_world` GPUs proving ONE witness together
+    int shard_rank = -1, shard_world = 0, shard_log_g = 0, shard_stage = 0;
     // proving lanes: emails are dealt round-robin to `n_lanes` streams, each with its own NTT vectors and MSM
     // workspace, so that the latency-bound tails of one email's kernels overlap the saturating kernels of another
     // Each lane owns two streams: `st` (high priority) carries the latency- / memory-bound kernels, `heavy` (low
@@ -1120,6 +1122,166 @@ static void load_witness(zke_ctx* x, zke_ctx::Slot& S, const uint8_t* wtns, size
     S.loaded = (uint32_t)batch;
 }
 
+// ------------------------------------------------------------------------------------------------ sharded proving
+// One proof across G = 2, 4 or 8 GPUs (BASELINE configs[3]/[4]).  Every GPU holds the key and the
+// witness; the work of the proof is partitioned:
+//   * the quotient: the N-point transforms are split 4-step style.  The vectors live at their global positions; a GPU
+//     works either on its ROW block (positions [rank * M, (rank + 1) * M), M = N / G) or on its COLUMN range (columns
+//     [rank * M / G, (rank + 1) * M / G) of every block).  begin: mat-vec for the rows of the column range + the top
+//     log2 G inverse stages (cross-block, in registers).  [exchange columns -> rows, done by the caller with NCCL
+//     all-to-all on the device pointers of zke_shard_vector]  mid: the block-local inverse stages, coset scale and
+//     block-local forward stages.  [exchange rows -> columns]  end: the top forward stages and a o b - c on the column
+//     range: this GPU's share of the H scalars (zero elsewhere);
+//   * the multi-exponentiations: A, B1, C, B2 over the contiguous point range [rank m / G, (rank + 1) m / G), H over the
+//     column range; each GPU finishes its partial sums to five affine points (ZKE_SHARD_PARTIAL_BYTES);
+//   * combine (host): the partial points of all GPUs (an all-gather of 388 bytes per GPU) are added and the proof is
+//     assembled - the group law makes the result bit-identical to the single-GPU proof.
+static void shard_geometry(const zke_ctx* x, int& log_m, int& log_cols, uint32_t& col0) {
+    log_m = (int)x->zkey->log_n - x->shard_log_g;
+    log_cols = log_m - x->shard_log_g;
+    col0 = (uint32_t)x->shard_rank << log_cols;
+}
+
+static void shard_begin(zke_ctx* x, int rank, int world) {
+    const zke_zkey* zk = x->zkey;
+    if (!zk) throw std::runtime_error("context was opened without a proving key");
+    require_idle(x);
+    int log_g = 0;
+    while ((1 << log_g) < world) ++log_g;
+    if (world < 2 || world > 8 || (1 << log_g) != world) throw std::runtime_error("sharded proving supports 2, 4 or 8 GPUs");
+    if (rank < 0 || rank >= world) throw std::runtime_error("bad shard rank");
+    if ((int)zk->log_n < 2 * log_g + 10) throw std::runtime_error("domain too small to shard (use batch parallelism)");
+    zke_ctx::Slot& S = x->slots[0];
+    if (S.loaded < 1) throw std::runtime_error("no witness loaded (call zke_witness / zke_load_witness on every rank first)");
+    CUDA_OK(cudaSetDevice(x->device));
+    x->shard_rank = rank; x->shard_world = world; x->shard_log_g = log_g;
+    int log_m, log_cols; uint32_t col0;
+    shard_geometry(x, log_m, log_cols, col0);
+    zke_ctx::Lane& L = x->lanes[0];
+    cudaStream_t st = L.st;
+    CUDA_OK(cudaStreamSynchronize(x->stream));
+    uint32_t* flag = (uint32_t*)(S.results.p + ZKE_RES_FLAG_OFF);
+    CUDA_OK(cudaMemsetAsync(flag, 0xff, 4, st));
+    dev::RowMap map;
+    map.log_cols = log_cols; map.log_m = log_m; map.col0 = col0;
+    const uint32_t n_rows = (uint32_t)world << log_cols;
+    dev::launch_build_ab(x->r1cs, S.w_all.p, L.va.p, L.vb.p, L.vc.p, n_rows, flag, st, &map);
+    const uint32_t n_cols = 1u << log_cols;
+    dev::launch_intt_cross(L.va.p, x->ntt, log_g, col0, n_cols, st);
+    dev::launch_intt_cross(L.vb.p, x->ntt, log_g, col0, n_cols, st);
+    dev::launch_intt_cross(L.vc.p, x->ntt, log_g, col0, n_cols, st);
+    CHECK_LAUNCH();
+    CUDA_OK(cudaStreamSynchronize(st));
+    x->shard_stage = 1;
+}
+
+static void shard_mid(zke_ctx* x) {
+    if (x->shard_stage != 1) throw std::runtime_error("zke_shard_mid out of order");
+    CUDA_OK(cudaSetDevice(x->device));
+    int log_m, log_cols; uint32_t col0;
+    shard_geometry(x, log_m, log_cols, col0);
+    zke_ctx::Lane& L = x->lanes[0];
+    cudaStream_t st = L.st;
+    const size_t block_off = ((size_t)x->shard_rank << log_m);
+    for (uint8_t* v : {L.va.p, L.vb.p, L.vc.p}) {
+        dev::launch_intt_dif_block(v + 32 * block_off, x->ntt, log_m, x->coset_scale.p + 64 * block_off, st);
+        dev::launch_ntt_dit_block(v + 32 * block_off, x->ntt, log_m, st);
+    }
+    CHECK_LAUNCH();
+    CUDA_OK(cudaStreamSynchronize(st));
+    x->shard_stage = 2;
+}
+
+static void put_g1(uint8_t* dst, const G1AffineH& p) { write_fq(dst, p.x); write_fq(dst + 32, p.y); }
+
+static void shard_end(zke_ctx* x, uint8_t* partial_out, uint8_t* publics_out) {
+    if (x->shard_stage != 2) throw std::runtime_error("zke_shard_end out of order");
+    const zke_zkey* zk = x->zkey;
+    CUDA_OK(cudaSetDevice(x->device));
+    int log_m, log_cols; uint32_t col0;
+    shard_geometry(x, log_m, log_cols, col0);
+    zke_ctx::Slot& S = x->slots[0];
+    zke_ctx::Lane& L = x->lanes[0];
+    cudaStream_t st = L.st;
+    const uint32_t N = 1u << zk->log_n, m = x->n_vars, l = x->n_public;
+    const int G = x->shard_world, log_g = x->shard_log_g;
+    const uint32_t n_cols = 1u << log_cols;
+    dev::launch_ntt_cross(L.va.p, x->ntt, log_g, col0, n_cols, st);
+    dev::launch_ntt_cross(L.vb.p, x->ntt, log_g, col0, n_cols, st);
+    dev::launch_ntt_cross(L.vc.p, x->ntt, log_g, col0, n_cols, st);
+    CUDA_OK(cudaMemsetAsync(L.vd.p, 0, (size_t)N * 32, st));
+    dev::launch_quotient_cols(L.va.p, L.vb.p, L.vc.p, L.vd.p, (int)zk->log_n, log_g, col0, (uint32_t)log_cols, st);
+    CHECK_LAUNCH();
+    // witness multi-exponentiations over this GPU's point range, H over its columns (all other scalars are zero)
+    const uint32_t lo = (uint32_t)((uint64_t)m * x->shard_rank / G), hi = (uint32_t)((uint64_t)m * (x->shard_rank + 1) / G);
+    const uint8_t* w = S.w_all.p;
+    uint8_t* res = S.results.p;
+    dev::MsmPlan<dev::Fq>::run(zk->A.p + 64ull * lo, w + 32ull * lo, hi - lo, x->cfg_w, L.msm_ws.p, res + 0 * ZKE_RES_G1_BLOCK, st);
+    dev::MsmPlan<dev::Fq>::run(zk->B1.p + 64ull * lo, w + 32ull * lo, hi - lo, x->cfg_w, L.msm_ws.p, res + 1 * ZKE_RES_G1_BLOCK, st);
+    dev::MsmPlan<dev::Fq>::run(zk->C.p + 64ull * lo, w + 32ull * lo, hi - lo, x->cfg_w, L.msm_ws.p, res + 2 * ZKE_RES_G1_BLOCK, st);
+    dev::MsmPlan<dev::Fq2>::run(zk->B2.p + 128ull * lo, w + 32ull * lo, hi - lo, x->cfg_w, L.msm_ws.p, res + 4 * ZKE_RES_G1_BLOCK, st);
+    dev::MsmPlan<dev::Fq>::run(zk->H.p, L.vd.p, N, x->cfg_h, L.msm_ws.p, res + 3 * ZKE_RES_G1_BLOCK, st);
+    CHECK_LAUNCH();
+    CUDA_OK(cudaMemcpyAsync(S.results_host, res, ZKE_RESULT_STRIDE, cudaMemcpyDeviceToHost, st));
+    if (l) CUDA_OK(cudaMemcpyAsync(S.publics_host, S.w_all.p + 32, (size_t)l * 32, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    const uint8_t* rh = S.results_host;
+    put_g1(partial_out + 0, finish_msm<Fq>(rh + 0 * ZKE_RES_G1_BLOCK, x->cfg_w));
+    put_g1(partial_out + 64, finish_msm<Fq>(rh + 1 * ZKE_RES_G1_BLOCK, x->cfg_w));
+    put_g1(partial_out + 128, finish_msm<Fq>(rh + 2 * ZKE_RES_G1_BLOCK, x->cfg_w));
+    put_g1(partial_out + 192, finish_msm<Fq>(rh + 3 * ZKE_RES_G1_BLOCK, x->cfg_h));
+    const G2AffineH b2 = finish_msm<Fq2>(rh + 4 * ZKE_RES_G1_BLOCK, x->cfg_w);
+    write_fq(partial_out + 256, b2.x.c0); write_fq(partial_out + 288, b2.x.c1); write_fq(partial_out + 320, b2.y.c0); write_fq(partial_out + 352, b2.y.c1);
+    memcpy(partial_out + 384, rh + ZKE_RES_FLAG_OFF, 4);     // first violated row among this GPU's rows (0xffffffff: none)
+    if (publics_out && l) memcpy(publics_out, S.publics_host, (size_t)l * 32);
+    x->shard_stage = 0;
+}
+
+static Fq fq_from_le(const uint8_t* b) {
+    U256 v;
+    memcpy(v.v, b, 32);
+    if (u256_cmp(v, fq_params().p) >= 0) throw std::runtime_error("partial point coordinate not reduced");
+    return Fq::from_u256(v);
+}
+
+// host only: sums the partial points of all GPUs and assembles the proof (same formulas as finish_prove)
+struct ShardKeyPoints { G1AffineH alpha1, beta1, delta1; G2AffineH beta2, delta2; };
+static int shard_combine(const ShardKeyPoints* zk, const uint8_t* partials, int world, const uint8_t* rs, uint8_t* out, int32_t* status) {
+    G1JacH sa = G1JacH::inf(), sb1 = G1JacH::inf(), sc = G1JacH::inf(), sh = G1JacH::inf();
+    G2JacH sb2 = G2JacH::inf();
+    uint32_t first_bad = 0xffffffffu;
+    for (int r = 0; r < world; ++r) {
+        const uint8_t* p = partials + (size_t)ZKE_SHARD_PARTIAL_BYTES * r;
+        auto g1 = [&](const uint8_t* q) { return G1AffineH{fq_from_le(q), fq_from_le(q + 32)}; };
+        const G1AffineH a = g1(p), b1 = g1(p + 64), c = g1(p + 128), h = g1(p + 192);
+        const G2AffineH b2{Fq2{fq_from_le(p + 256), fq_from_le(p + 288)}, Fq2{fq_from_le(p + 320), fq_from_le(p + 352)}};
+        if (!g1_on_curve(a) || !g1_on_curve(b1) || !g1_on_curve(c) || !g1_on_curve(h) || !g2_on_curve(b2)) throw std::runtime_error("partial point not on the curve");
+        sa = sa.add_affine(a); sb1 = sb1.add_affine(b1); sc = sc.add_affine(c); sh = sh.add_affine(h); sb2 = sb2.add_affine(b2);
+        uint32_t f;
+        memcpy(&f, p + 384, 4);
+        first_bad = std::min(first_bad, f);
+    }
+    if (status) *status = first_bad == 0xffffffffu ? -1 : (int32_t)first_bad;
+    if (first_bad != 0xffffffffu) { memset(out, 0, 256); return 1; }
+    U256 r, s;
+    if (rs) { memcpy(r.v, rs, 32); memcpy(s.v, rs + 32, 32); }
+    else { random_scalar(r); random_scalar(s); }
+    if (u256_cmp(r, fr_params().p) >= 0 || u256_cmp(s, fr_params().p) >= 0) throw std::runtime_error("r / s not reduced mod the group order");
+    const G1JacH alpha1 = G1JacH::from_affine(zk->alpha1), beta1 = G1JacH::from_affine(zk->beta1), delta1 = G1JacH::from_affine(zk->delta1);
+    const G2JacH beta2 = G2JacH::from_affine(zk->beta2), delta2 = G2JacH::from_affine(zk->delta2);
+    G1JacH pa = alpha1.add(sa).add(delta1.mul(r));
+    G2JacH pb2 = beta2.add(sb2).add(delta2.mul(s));
+    G1JacH pb1 = beta1.add(sb1).add(delta1.mul(s));
+    U256 rs_prod = (Fr::from_u256(r) * Fr::from_u256(s)).to_u256();
+    G1JacH pc = sc.add(sh).add(pa.mul(s)).add(pb1.mul(r)).add(delta1.mul(rs_prod).neg());
+    G1AffineH A = pa.to_affine(), C = pc.to_affine();
+    G2AffineH B = pb2.to_affine();
+    write_fq(out + 0, A.x); write_fq(out + 32, A.y);
+    write_fq(out + 64, B.x.c0); write_fq(out + 96, B.x.c1); write_fq(out + 128, B.y.c0); write_fq(out + 160, B.y.c1);
+    write_fq(out + 192, C.x); write_fq(out + 224, C.y);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
@@ -1365,6 +1527,47 @@ int zke_fullprove(zke_ctx* x, const uint8_t* inputs, size_t batch, const uint8_t
         int bad = do_prove(x, S, batch, rs, proofs_out, publics_out, status, msg);
         if (bad) { set_err(err, errcap, msg); return bad; }
         return 0;
+    } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+
+int zke_shard_begin(zke_ctx* x, int rank, int world, char* err, size_t errcap) {
+    try { if (!x) throw std::runtime_error("null context"); shard_begin(x, rank, world); return 0; }
+    catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+void* zke_shard_vector(zke_ctx* x, int which, size_t* n_elems) {
+    if (!x || !x->zkey || which < 0 || which > 2 || x->lanes_alloc < 1) return nullptr;
+    if (n_elems) *n_elems = (size_t)1 << x->zkey->log_n;
+    zke_ctx::Lane& L = x->lanes[0];
+    return which == 0 ? L.va.p : (which == 1 ? L.vb.p : L.vc.p);
+}
+int zke_shard_mid(zke_ctx* x, char* err, size_t errcap) {
+    try { if (!x) throw std::runtime_error("null context"); shard_mid(x); return 0; }
+    catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+int zke_shard_end(zke_ctx* x, uint8_t* partial_out, uint8_t* publics_out, char* err, size_t errcap) {
+    try { if (!x || !partial_out) throw std::runtime_error("null argument"); shard_end(x, partial_out, publics_out); return 0; }
+    catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+int zke_shard_combine(const zke_zkey* z, const uint8_t* partials, int world, const uint8_t* rs, uint8_t* proof_out, int32_t* status,
+                      char* err, size_t errcap) {
+    try {
+        if (!z || !partials || !proof_out || world < 1) throw std::runtime_error("bad argument");
+        const ShardKeyPoints kp{z->alpha1, z->beta1, z->delta1, z->beta2, z->delta2};
+        int bad = shard_combine(&kp, partials, world, rs, proof_out, status);
+        if (bad) set_err(err, errcap, "Assert Failed: constraint " + std::to_string(status ? *status : 0));
+        return bad;
+    } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+int zke_shard_combine_raw(const uint8_t* key_points, const uint8_t* partials, int world, const uint8_t* rs, uint8_t* proof_out,
+                          int32_t* status, char* err, size_t errcap) {
+    try {
+        if (!key_points || !partials || !proof_out || world < 1) throw std::runtime_error("bad argument");
+        auto g1 = [&](const uint8_t* q) { return G1AffineH{fq_from_le(q), fq_from_le(q + 32)}; };
+        auto g2 = [&](const uint8_t* q) { return G2AffineH{Fq2{fq_from_le(q), fq_from_le(q + 32)}, Fq2{fq_from_le(q + 64), fq_from_le(q + 96)}}; };
+        const ShardKeyPoints kp{g1(key_points), g1(key_points + 64), g1(key_points + 128), g2(key_points + 192), g2(key_points + 320)};
+        int bad = shard_combine(&kp, partials, world, rs, proof_out, status);
+        if (bad) set_err(err, errcap, "Assert Failed: constraint " + std::to_string(status ? *status : 0));
+        return bad;
     } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
 }
 

@@ -23,9 +23,11 @@ __device__ __forceinline__ Fr row_dot(const uint32_t* ptr, const uint2* terms, c
 // from a and b rather than from the C matrix) - fused here so that no separate Hadamard pass is needed.
 __global__ void __launch_bounds__(256)
 build_ab_kernel(DevR1cs R, const uint8_t* __restrict__ w, uint8_t* __restrict__ a_out, uint8_t* __restrict__ b_out,
-                uint8_t* __restrict__ c_out, uint32_t n, uint32_t* first_bad) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                uint8_t* __restrict__ c_out, uint32_t n, uint32_t* first_bad, RowMap map) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    // sharded proving: thread t works on row (block, column) of the column range this GPU holds
+    const uint32_t i = map.log_cols < 0 ? t : (((t >> map.log_cols) << map.log_m) + map.col0 + (t & ((1u << map.log_cols) - 1)));
     Fr a = Fr::zero(), b = Fr::zero(), c = Fr::zero();
     if (i < R.n_constraints) {
         a = row_dot(R.a_ptr, R.a_terms, R.coef_r, w, i);
@@ -63,8 +65,11 @@ void launch_check_witness(const uint8_t* w_all, size_t stride_elems, uint32_t n_
     ZKE_COUNT_LAUNCH(1);
 }
 
-void launch_build_ab(const DevR1cs& R, const uint8_t* w, uint8_t* a_out, uint8_t* b_out, uint8_t* c_out, uint32_t n, uint32_t* first_bad, cudaStream_t st) {
-    build_ab_kernel<<<(n + 255) / 256, 256, 0, st>>>(R, w, a_out, b_out, c_out, n, first_bad);
+void launch_build_ab(const DevR1cs& R, const uint8_t* w, uint8_t* a_out, uint8_t* b_out, uint8_t* c_out, uint32_t n, uint32_t* first_bad, cudaStream_t st,
+                     const RowMap* map) {
+    RowMap m;
+    if (map) m = *map;
+    build_ab_kernel<<<(n + 255) / 256, 256, 0, st>>>(R, w, a_out, b_out, c_out, n, first_bad, m);
     ZKE_COUNT_LAUNCH(1);
 }
 

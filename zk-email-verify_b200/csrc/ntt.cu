@@ -27,7 +27,7 @@ struct Planar {
 template <bool DIF>
 __global__ void __launch_bounds__(1 << (MAX_TILE_LOG - 1))
 ntt_pass_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, const uint8_t* __restrict__ scale,
-                int log_n, int s_lo, int s_hi, int tile_log) {
+                int log_n, int s_lo, int s_hi, int tile_log) {   // log_n: size of the transform the twiddle table belongs to
     extern __shared__ uint32_t smem[];
     const int TILE = 1 << tile_log;
     const int NTT_THREADS = TILE / 2;
@@ -183,7 +183,7 @@ ntt_pass_fast_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw,
 }
 
 template <bool DIF>
-static bool launch_fast(uint8_t* data, const uint8_t* tw, const uint8_t* scale, int log_n, int s_lo, int s_hi, cudaStream_t st) {
+static bool launch_fast(uint8_t* data, const uint8_t* tw, const uint8_t* scale, int log_n, int s_lo, int s_hi, cudaStream_t st, int log_tw) {
     if (log_n < 10) return false;
     const int k = s_hi - s_lo + 1;
     const uint32_t blocks = 1u << (log_n - 10);
@@ -191,8 +191,8 @@ static bool launch_fast(uint8_t* data, const uint8_t* tw, const uint8_t* scale, 
     if (strided && s_lo < 10 - k) return false;
 #define ZKE_NTT_CASE(KK)                                                                                            \
     case KK:                                                                                                       \
-        if (strided) ntt_pass_fast_kernel<DIF, KK, true><<<blocks, 512, 0, st>>>(data, tw, scale, log_n, s_lo);     \
-        else ntt_pass_fast_kernel<DIF, KK, false><<<blocks, 512, 0, st>>>(data, tw, scale, log_n, s_lo);            \
+        if (strided) ntt_pass_fast_kernel<DIF, KK, true><<<blocks, 512, 0, st>>>(data, tw, scale, log_tw, s_lo);     \
+        else ntt_pass_fast_kernel<DIF, KK, false><<<blocks, 512, 0, st>>>(data, tw, scale, log_tw, s_lo);            \
         return true;
     switch (k) {
         ZKE_NTT_CASE(4) ZKE_NTT_CASE(5) ZKE_NTT_CASE(6) ZKE_NTT_CASE(7) ZKE_NTT_CASE(8)
@@ -215,30 +215,91 @@ static void plan(int log_n, int* lo, int* hi, int* n_pass) {
     *n_pass = passes;
 }
 
-void launch_intt_dif(uint8_t* data, const NttTables& T, const uint8_t* scale_bitrev, cudaStream_t st) {
+// `log_local` < T.log_n: the transform is the tail of a larger one - the 2^log_local elements at `data` are one of the
+// independent blocks left after the top T.log_n - log_local stages were done elsewhere (msm sharding across GPUs);
+// the twiddle tables are those of the full transform.
+static void intt_dif_impl(uint8_t* data, const NttTables& T, int log_local, const uint8_t* scale_bitrev, cudaStream_t st) {
     int lo[4], hi[4], np;
-    plan(T.log_n, lo, hi, &np);
+    plan(log_local, lo, hi, &np);
     ZKE_COUNT_LAUNCH(np);
-    const int tile_log = T.log_n < MAX_TILE_LOG ? T.log_n : MAX_TILE_LOG;
-    const uint32_t blocks = 1u << (T.log_n - tile_log);
+    const int tile_log = log_local < MAX_TILE_LOG ? log_local : MAX_TILE_LOG;
+    const uint32_t blocks = 1u << (log_local - tile_log);
     for (int p = 0; p < np; ++p) {
         const uint8_t* sc = p == np - 1 ? scale_bitrev : nullptr;
-        if (launch_fast<true>(data, T.tw_inv, sc, T.log_n, lo[p], hi[p], st)) continue;
+        if (launch_fast<true>(data, T.tw_inv, sc, log_local, lo[p], hi[p], st, T.log_n)) continue;
         ntt_pass_kernel<true><<<blocks, 1 << (tile_log - 1), 32u << tile_log, st>>>(data, T.tw_inv, sc, T.log_n, lo[p], hi[p], tile_log);
     }
 }
-
-void launch_ntt_dit(uint8_t* data, const NttTables& T, cudaStream_t st) {
+static void ntt_dit_impl(uint8_t* data, const NttTables& T, int log_local, cudaStream_t st) {
     int lo[4], hi[4], np;
-    plan(T.log_n, lo, hi, &np);
+    plan(log_local, lo, hi, &np);
     ZKE_COUNT_LAUNCH(np);
-    const int tile_log = T.log_n < MAX_TILE_LOG ? T.log_n : MAX_TILE_LOG;
-    const uint32_t blocks = 1u << (T.log_n - tile_log);
+    const int tile_log = log_local < MAX_TILE_LOG ? log_local : MAX_TILE_LOG;
+    const uint32_t blocks = 1u << (log_local - tile_log);
     for (int p = np - 1; p >= 0; --p) {
-        if (launch_fast<false>(data, T.tw_fwd, nullptr, T.log_n, lo[p], hi[p], st)) continue;
+        if (launch_fast<false>(data, T.tw_fwd, nullptr, log_local, lo[p], hi[p], st, T.log_n)) continue;
         ntt_pass_kernel<false><<<blocks, 1 << (tile_log - 1), 32u << tile_log, st>>>(data, T.tw_fwd, nullptr, T.log_n, lo[p], hi[p], tile_log);
     }
 }
+void launch_intt_dif(uint8_t* data, const NttTables& T, const uint8_t* scale_bitrev, cudaStream_t st) { intt_dif_impl(data, T, T.log_n, scale_bitrev, st); }
+void launch_ntt_dit(uint8_t* data, const NttTables& T, cudaStream_t st) { ntt_dit_impl(data, T, T.log_n, st); }
+void launch_intt_dif_block(uint8_t* block, const NttTables& T, int log_local, const uint8_t* scale_block, cudaStream_t st) { intt_dif_impl(block, T, log_local, scale_block, st); }
+void launch_ntt_dit_block(uint8_t* block, const NttTables& T, int log_local, cudaStream_t st) { ntt_dit_impl(block, T, log_local, st); }
+
+// ---- the top LOGG stages of a transform whose blocks live on different GPUs -------------------------------------------
+// Column layout: this GPU holds, for every one of the G = 2^LOGG blocks g, the columns [col0, col0 + n_cols) of the
+// block (element (g, j) at its global position g * M + j, M = N / G).  One thread per column does the LOGG butterfly
+// stages of distance M, 2M, ... in registers.  DIF (inverse transform): these are the FIRST stages, top down;
+// DIT (forward): the LAST stages, bottom up.
+template <bool DIF, int LOGG>
+__global__ void __launch_bounds__(128)
+ntt_cross_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, int log_n, uint32_t col0, uint32_t n_cols) {
+    constexpr int G = 1 << LOGG;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_cols) return;
+    const int log_m = log_n - LOGG;
+    const uint32_t j = col0 + t;
+    Fr x[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) x[g] = Fr::load(data + 32ull * (((uint32_t)g << log_m) + j));
+#pragma unroll
+    for (int step = 0; step < LOGG; ++step) {
+        const int sb = DIF ? (LOGG - 1 - step) : step;        // stage bit within the block index
+        const int st = log_m + sb;
+#pragma unroll
+        for (int g0 = 0; g0 < G; ++g0) {
+            if (g0 & (1 << sb)) continue;
+            const int g1 = g0 | (1 << sb);
+            const uint32_t idx0 = ((uint32_t)g0 << log_m) + j;
+            const uint64_t tw_i = (uint64_t)(idx0 & ((1u << st) - 1)) << (log_n - 1 - st);
+            const Fr w = Fr::load(tw + 64ull * tw_i), wq = Fr::load(tw + 64ull * tw_i + 32);
+            const Fr u = x[g0], v = x[g1];
+            if (DIF) {
+                x[g0] = u + v;
+                x[g1] = Fr::mul_shoup(u - v, w.v, wq.v);
+            } else {
+                const Fr y = Fr::mul_shoup(v, w.v, wq.v);
+                x[g0] = u + y;
+                x[g1] = u - y;
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) x[g].store(data + 32ull * (((uint32_t)g << log_m) + j));
+}
+template <bool DIF>
+static void launch_cross(uint8_t* data, const uint8_t* tw, int log_n, int log_g, uint32_t col0, uint32_t n_cols, cudaStream_t st) {
+    const uint32_t blocks = (n_cols + 127) / 128;
+    switch (log_g) {
+        case 1: ntt_cross_kernel<DIF, 1><<<blocks, 128, 0, st>>>(data, tw, log_n, col0, n_cols); break;
+        case 2: ntt_cross_kernel<DIF, 2><<<blocks, 128, 0, st>>>(data, tw, log_n, col0, n_cols); break;
+        case 3: ntt_cross_kernel<DIF, 3><<<blocks, 128, 0, st>>>(data, tw, log_n, col0, n_cols); break;
+        default: break;
+    }
+    ZKE_COUNT_LAUNCH(1);
+}
+void launch_intt_cross(uint8_t* data, const NttTables& T, int log_g, uint32_t col0, uint32_t n_cols, cudaStream_t st) { launch_cross<true>(data, T.tw_inv, T.log_n, log_g, col0, n_cols, st); }
+void launch_ntt_cross(uint8_t* data, const NttTables& T, int log_g, uint32_t col0, uint32_t n_cols, cudaStream_t st) { launch_cross<false>(data, T.tw_fwd, T.log_n, log_g, col0, n_cols, st); }
 
 // c = a o b   (Montgomery in/out)
 __global__ void hadamard_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ c, uint32_t n) {
@@ -261,6 +322,20 @@ __global__ void quotient_kernel(const uint8_t* __restrict__ a, const uint8_t* __
 }
 void launch_quotient(const uint8_t* a, const uint8_t* b, const uint8_t* c, uint8_t* d, uint32_t n, cudaStream_t st) {
     quotient_kernel<<<(n + 255) / 256, 256, 0, st>>>(a, b, c, d, n);
+    ZKE_COUNT_LAUNCH(1);
+}
+// the same on the columns [col0, col0 + 2^log_cols) of every block of 2^log_m elements (global positions)
+__global__ void quotient_cols_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, const uint8_t* __restrict__ c,
+                                     uint8_t* __restrict__ d, uint32_t n_threads, int log_m, int log_cols, uint32_t col0) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_threads) return;
+    const uint32_t i = ((t >> log_cols) << log_m) + col0 + (t & ((1u << log_cols) - 1));
+    Fr x = Fr::load(a + 32ull * i) * Fr::load(b + 32ull * i) - Fr::load(c + 32ull * i);
+    x.from_mont().store(d + 32ull * i);
+}
+void launch_quotient_cols(const uint8_t* a, const uint8_t* b, const uint8_t* c, uint8_t* d, int log_n, int log_g, uint32_t col0, uint32_t n_cols_log, cudaStream_t st) {
+    const uint32_t n_threads = (1u << log_g) << n_cols_log;
+    quotient_cols_kernel<<<(n_threads + 255) / 256, 256, 0, st>>>(a, b, c, d, n_threads, log_n - log_g, (int)n_cols_log, col0);
     ZKE_COUNT_LAUNCH(1);
 }
 

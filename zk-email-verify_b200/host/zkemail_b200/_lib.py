@@ -96,3 +96,11 @@ zke_selftest_fpmul_hint = _sig("zke_selftest_fpmul_hint", c_int, [c_u32, c_u32, 
 
 (SEC_ALPHA1, SEC_BETA1, SEC_DELTA1, SEC_BETA2, SEC_GAMMA2, SEC_DELTA2) = (101, 102, 103, 104, 105, 106)
 (SEC_IC, SEC_A, SEC_B1, SEC_B2, SEC_C, SEC_H) = (3, 5, 6, 7, 8, 9)
+
+SHARD_PARTIAL_BYTES = 388
+zke_shard_begin = _sig("zke_shard_begin", c_int, [c_void_p, c_int, c_int, c_char_p, c_size_t])
+zke_shard_vector = _sig("zke_shard_vector", c_void_p, [c_void_p, c_int, ctypes.POINTER(c_size_t)])
+zke_shard_mid = _sig("zke_shard_mid", c_int, [c_void_p, c_char_p, c_size_t])
+zke_shard_end = _sig("zke_shard_end", c_int, [c_void_p, c_void_p, c_void_p, c_char_p, c_size_t])
+zke_shard_combine = _sig("zke_shard_combine", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, ctypes.POINTER(ctypes.c_int32), c_char_p, c_size_t])
+zke_shard_combine_raw = _sig("zke_shard_combine_raw", c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, ctypes.POINTER(ctypes.c_int32), c_char_p, c_size_t])

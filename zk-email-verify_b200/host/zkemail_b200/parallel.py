@@ -42,3 +42,108 @@ def gather_proofs(local_proofs: bytes, local_publics: bytes, n_items: int, n_pub
             proofs += data[rec * i: rec * i + 256]
             publics += data[rec * i + 256: rec * (i + 1)]
     return bytes(proofs), bytes(publics)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Intra-proof sharding (BASELINE configs[3] / [4]): ONE proof across 2, 4 or 8 GPUs.
+# The engine does the per-GPU work (zke_shard_begin / _mid / _end, include/zkemail_b200.h); the exchanges between the
+# steps are collectives on the engine's device vectors, carried by torch.distributed (NCCL over NVLink on GPUs):
+#   exchange 1 / 2 : all-to-all "columns -> rows" / "rows -> columns" of the three N x 32-byte evaluation vectors -
+#                    every GPU sends (world - 1) / world^2 of a vector to the others: 3 x 2 x N x 32 x (world-1)/world
+#                    bytes cross NVLink per proof in total (352 MiB at N = 2^24, world = 8)
+#   all-gather     : 388 bytes per GPU (five partial points + the constraint-check word)
+# The index logic of the exchanges lives in shard_exchange() and works on any tensor (CPU tensors in the gloo tests).
+def shard_views(vec, rank: int, world: int):
+    """Views of an [N, ...] tensor: (rows, cols) where rows[q] = (block rank, columns of q) and cols[g] = (block g,
+    columns of rank) - the pieces GPU `rank` exchanges with GPU q / g."""
+    n = vec.shape[0]
+    if n % (world * world):
+        raise ValueError("vector length must be a multiple of world^2")
+    m, c = n // world, n // (world * world)
+    rows = [vec[rank * m + q * c: rank * m + (q + 1) * c] for q in range(world)]
+    cols = [vec[g * m + rank * c: g * m + (rank + 1) * c] for g in range(world)]
+    return rows, cols
+
+
+def shard_exchange(vec, rank: int, world: int, to_rows: bool, group=None):
+    """In-place all-to-all on a vector laid out at global positions: to_rows=True sends this GPU's column range of every
+    block g to GPU g (afterwards the GPU holds its whole row block); to_rows=False is the inverse."""
+    import torch.distributed as dist
+    rows, cols = shard_views(vec, rank, world)
+    send, recv = (cols, rows) if to_rows else (rows, cols)
+    # the diagonal piece (block rank, columns of rank) is both sent to and received from this GPU itself: clone the
+    # send side so that source and destination never alias
+    send = [t.clone() for t in send]
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all(recv, send, group=group)       # one grouped NCCL all-to-all over NVLink
+        return
+    # backends without all-to-all (gloo in the CPU tests): the same pattern as paired sends / receives
+    recv[rank].copy_(send[rank])
+    ops = []
+    for peer in range(world):
+        if peer != rank:
+            ops.append(dist.P2POp(dist.isend, send[peer], peer, group))
+            ops.append(dist.P2POp(dist.irecv, recv[peer], peer, group))
+    for work in dist.batch_isend_irecv(ops):
+        work.wait()
+
+
+class _DevVec:
+    """Zero-copy torch view of an engine-owned device vector (N x 32 bytes) via __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, n_elems: int):
+        self.__cuda_array_interface__ = {"shape": (n_elems, 32), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def prove_sharded(ctx, packed_input: bytes, rs: bytes | None = None, group=None):
+    """One Groth16 proof computed by all ranks of `group` together (every rank passes the same input and, for a
+    reproducible proof, the same 64-byte (r, s)).  Returns (proof bytes, public signal bytes, status) on every rank."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from . import _lib as L
+    from .engine import AssertFailed
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    err = ctypes.create_string_buffer(L.ERRCAP)
+
+    def ok(rc):
+        if rc != 0:
+            raise L.ZkeError(err.value.decode())
+
+    ctx.witness(packed_input, 1, want_witness=False, raise_on_fail=False)       # replicated: every GPU needs the witness
+    ok(L.zke_shard_begin(ctx.handle, rank, world, err, L.ERRCAP))
+    n = L.c_size_t()
+    vecs = []
+    for which in range(3):
+        ptr = L.zke_shard_vector(ctx.handle, which, ctypes.byref(n))
+        vecs.append(torch.as_tensor(_DevVec(ptr, n.value), device=torch.device("cuda", ctx.device)))
+    for v in vecs:
+        shard_exchange(v, rank, world, True, group)
+    torch.cuda.synchronize()
+    ok(L.zke_shard_mid(ctx.handle, err, L.ERRCAP))
+    for v in vecs:
+        shard_exchange(v, rank, world, False, group)
+    torch.cuda.synchronize()
+    partial = ctypes.create_string_buffer(L.SHARD_PARTIAL_BYTES)
+    publics = ctypes.create_string_buffer(max(1, 32 * ctx.n_public))
+    ok(L.zke_shard_end(ctx.handle, partial, publics, err, L.ERRCAP))
+    mine = torch.frombuffer(bytearray(partial.raw), dtype=torch.uint8).cuda(ctx.device)
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine, group=group)
+    allp = b"".join(bytes(t.cpu().numpy()) for t in gathered)
+    return combine_partials(ctx.zkey, allp, world, rs, publics.raw[: 32 * ctx.n_public])
+
+
+def combine_partials(zkey, partials: bytes, world: int, rs: bytes | None, publics: bytes):
+    import ctypes
+    from . import _lib as L
+    from .engine import AssertFailed
+    proof = ctypes.create_string_buffer(256)
+    status = ctypes.c_int32(-1)
+    err = ctypes.create_string_buffer(L.ERRCAP)
+    rc = L.zke_shard_combine(zkey.handle, partials, world, rs, proof, ctypes.byref(status), err, L.ERRCAP)
+    if rc < 0:
+        raise L.ZkeError(err.value.decode())
+    if rc > 0:
+        raise AssertFailed(err.value.decode())
+    return proof.raw, publics, status.value
