@@ -295,12 +295,12 @@ def main():
                         "entry, see DESIGN.md section 5"}
     # the pipe that actually bounds the kernel: integer multiply (IMAD.WIDE).  achieved = executed fmaheavy warp
     # instructions of one launch (ncu capture, profiles/roofline_traffic.json) / live kernel time; peak = the measured
-    # IMAD.WIDE issue rate of this GPU (scripts/pipe_peaks.cu -> profiles/pipe_peaks_r02.json)
+    # IMAD.WIDE rate of this GPU inside the Montgomery product (scripts/field_peaks.cu -> profiles/field_peaks_r02.json)
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             t = json.load(f)
-        with open(os.path.join(ROOT, "profiles", "pipe_peaks_r02.json")) as f:
-            pk = json.load(f)["results"]["imad_wide"]["giga_warp_instr_per_s"]
+        with open(os.path.join(ROOT, "profiles", "field_peaks_r02.json")) as f:
+            pk = json.load(f)["results"]["mul_cios"]["giga_warp_imad_wide_per_s"]
         ach = float(t["fmaheavy_warp_instr"]) / (kernel_ms / 1e3) / 1e9
         roofline["imad"] = {"achieved": ach, "peak": pk, "unit": "G warp-IMAD.WIDE/s", "frac": ach / pk,
                             "warp_instr_per_launch": float(t["fmaheavy_warp_instr"])}

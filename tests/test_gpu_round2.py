@@ -277,3 +277,27 @@ def test_config5_one_email_2pow24():
     with pytest.raises(z.AssertFailed, match="Assert Failed"):
         ctx.fullprove(c.pack_inputs(bad), 1)
     ctx.close()
+
+
+def test_registry_refuses_toy_keys_and_serves_loaded_ones(tmp_path):
+    """generateProof / verifyProof mirror (chunked-zkey.ts:76-105): a key from the seeded toy setup is refused unless
+    explicitly allowed; the same key written as the fork's chunk files and loaded back is served."""
+    import hashlib
+    c = z.Circuit("Sha256Bytes", [64])
+    toy = z.Zkey(c, seed=11, device=0)
+    with pytest.raises(z.InsecureKeyError):
+        z.register_circuit("sha-toy", c, toy)
+    chunks = B.write_zkey_chunks(toy)
+    paths = []
+    for suffix in "bcdefghijk":
+        p = tmp_path / ("sha.zkey" + suffix)
+        p.write_bytes(chunks["zkey" + suffix])
+        paths.append(str(p))
+    z.register_zkey_files("sha", c, paths)
+    padded, plen = z.sha256_pad(b"registry", 64)
+    out = z.generate_proof({"paddedIn": list(padded), "paddedInLength": plen}, "https://example.invalid/", "sha")
+    digest = hashlib.sha256(b"registry").digest()
+    assert out["publicSignals"] == [str((b >> (7 - j)) & 1) for b in digest for j in range(8)]
+    assert z.verify_proof(out["proof"], out["publicSignals"], "https://example.invalid/", "sha")
+    with pytest.raises(KeyError, match="after 3 retries"):
+        z.generate_proof({}, "https://example.invalid/", "unknown-circuit")

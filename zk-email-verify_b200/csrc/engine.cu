@@ -762,7 +762,15 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         const Fr omega = fr_root_of_unity(log_n), omega_inv = omega.inv();
         const Fr g = fr_root_of_unity(log_n + 1);
         const Fr n_inv = Fr::from_u64(N).inv();
-        std::vector<ShoupPair> fw(std::max<size_t>(1, N / 2)), iv(std::max<size_t>(1, N / 2)), cs(N);
+        // constants of the transforms: Montgomery form (32 bytes) or fixed-operand pairs (64 bytes) - ZKE_NTT_SHOUP
+        bool shoup = false;
+        if (const char* e = getenv("ZKE_NTT_SHOUP")) shoup = atoi(e) != 0;
+        const size_t esz = shoup ? 64 : 32;
+        std::vector<uint8_t> fw(esz * std::max<size_t>(1, N / 2)), iv(esz * std::max<size_t>(1, N / 2)), cs(esz * N);
+        auto put = [&](std::vector<uint8_t>& tab, size_t i, const Fr& w) {
+            if (shoup) { const ShoupPair sp = shoup_pair(w); memcpy(&tab[64 * i], sp.w.v, 32); memcpy(&tab[64 * i + 32], sp.wq.v, 32); }
+            else memcpy(&tab[32 * i], w.m.v, 32);
+        };
         const unsigned T = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
         std::vector<std::thread> th;
         for (unsigned t = 0; t < T; ++t) {
@@ -771,7 +779,7 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                 if (beg < end) {
                     U256 e = {{(uint64_t)beg, 0, 0, 0}};
                     Fr a = omega.pow(e), b = omega_inv.pow(e);
-                    for (size_t i = beg; i < end; ++i) { fw[i] = shoup_pair(a); iv[i] = shoup_pair(b); a = a * omega; b = b * omega_inv; }
+                    for (size_t i = beg; i < end; ++i) { put(fw, i, a); put(iv, i, b); a = a * omega; b = b * omega_inv; }
                 }
                 beg = N * t / T; end = N * (t + 1) / T;
                 if (beg < end) {
@@ -780,16 +788,16 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                     for (size_t j = beg; j < end; ++j) {
                         size_t p = 0;
                         for (unsigned bit = 0; bit < log_n; ++bit) if (j & ((size_t)1 << bit)) p |= (size_t)1 << (log_n - 1 - bit);
-                        cs[p] = shoup_pair(a);
+                        put(cs, p, a);
                         a = a * g;
                     }
                 }
             });
         }
         for (auto& t : th) t.join();
-        if (N == 1) { fw[0] = shoup_pair(Fr::one()); iv[0] = shoup_pair(Fr::one()); }
+        if (N == 1) { put(fw, 0, Fr::one()); put(iv, 0, Fr::one()); }
         x->tw_fwd.upload(fw); x->tw_inv.upload(iv); x->coset_scale.upload(cs);
-        x->ntt.tw_fwd = x->tw_fwd.p; x->ntt.tw_inv = x->tw_inv.p; x->ntt.log_n = (int)log_n;
+        x->ntt.tw_fwd = x->tw_fwd.p; x->ntt.tw_inv = x->tw_inv.p; x->ntt.log_n = (int)log_n; x->ntt.shoup = shoup;
         x->cfg_w = dev::msm_config_witness();
         x->cfg_h = zk->cfg_h;
         size_t ws = std::max(dev::MsmPlan<dev::Fq>::workspace_bytes(x->n_vars, x->cfg_w),
@@ -1184,7 +1192,7 @@ static void shard_mid(zke_ctx* x) {
     cudaStream_t st = L.st;
     const size_t block_off = ((size_t)x->shard_rank << log_m);
     for (uint8_t* v : {L.va.p, L.vb.p, L.vc.p}) {
-        dev::launch_intt_dif_block(v + 32 * block_off, x->ntt, log_m, x->coset_scale.p + 64 * block_off, st);
+        dev::launch_intt_dif_block(v + 32 * block_off, x->ntt, log_m, x->coset_scale.p + (x->ntt.shoup ? 64 : 32) * block_off, st);
         dev::launch_ntt_dit_block(v + 32 * block_off, x->ntt, log_m, st);
     }
     CHECK_LAUNCH();

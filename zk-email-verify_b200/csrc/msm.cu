@@ -163,6 +163,24 @@ static __global__ void digit_scatter_kernel(const uint8_t* __restrict__ scalars,
         });
     }
 }
+// The same counting-sort scatter, moving the POINTS instead of their indices (batched-affine path): thread t reads
+// point t of every table level - consecutive threads read consecutive points, so the 3.5 GB table streams in coalesced
+// - and writes the (sign-adjusted) point to its place in bucket order.  The sweeps then work on flat arrays only.
+template <class F>
+__global__ void __launch_bounds__(256)
+digit_scatter_points_kernel(const uint8_t* __restrict__ scalars, uint32_t count, Digits D, const uint32_t* __restrict__ offsets,
+                            uint32_t* cursor, const uint8_t* __restrict__ points, Affine<F>* __restrict__ sorted) {
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+        Fr s = load_scalar(scalars, idx);
+        for_each_digit(s, D, [&](int j, uint32_t b, bool neg) {
+            const uint32_t bucket = (uint32_t)j * D.window_bucket_stride + b;
+            const uint32_t pos = offsets[bucket] + atomicAdd(&cursor[bucket], 1u);
+            Affine<F> p = Affine<F>::load(points + sizeof(Affine<F>) * ((size_t)j * D.window_point_stride + idx));
+            if (neg) p.y = p.y.neg();
+            p.store(sorted + pos);
+        });
+    }
+}
 
 // ---------------------------------------------------------------- exclusive scan over the bucket array
 // out[i] = sum_{k<i} f(in[k]); out[n] = total.  f = identity (chunk == 0) or ceil(x / chunk).
@@ -327,8 +345,9 @@ partial_pass_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__
 
 // one thread per GROUP consecutive buckets of one window: sum_b (b+1) B_b restricted to the group, as
 // T + first_index * S with T the in-group weighted sum and S the plain sum
-// AFFINE: the items are affine points (outputs of the batched-affine sweeps) and are added with mixed additions
-template <class F, bool AFFINE>
+// ITEMS = 0: XYZZ partial sums located by chunk_off (per-chunk sums of the XYZZ bucket kernel); 1: one XYZZ sum per
+// bucket at index `bucket` (batched-affine path after bucket_finish_kernel)
+template <class F, int ITEMS>
 __global__ void __launch_bounds__(128)
 group_sum_kernel(const uint8_t* __restrict__ partial, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ chunk_off,
                  uint32_t half, uint32_t n_groups_total, uint32_t CHUNK, uint32_t levels, uint32_t GROUP, uint8_t* group_out) {
@@ -340,10 +359,11 @@ group_sum_kernel(const uint8_t* __restrict__ partial, const uint32_t* __restrict
     XYZZ<F> running = XYZZ<F>::inf(), total = XYZZ<F>::inf();
     for (uint32_t b = hi; b-- > lo;) {
         const uint32_t bucket = window * half + b;
-        const uint32_t nch = scan_f(hist[bucket], CHUNK, levels);
-        for (uint32_t i = 0; i < nch; ++i) {
-            if (AFFINE) running.madd(Affine<F>::load(partial + sizeof(Affine<F>) * (size_t)(chunk_off[bucket] + i)), false);
-            else running.add(XYZZ<F>::load(partial + sizeof(XYZZ<F>) * (size_t)(chunk_off[bucket] + i)));
+        if (ITEMS == 1) {
+            if (hist[bucket]) running.add(XYZZ<F>::load(partial + sizeof(XYZZ<F>) * (size_t)bucket));
+        } else {
+            const uint32_t nch = scan_f(hist[bucket], CHUNK, levels);
+            for (uint32_t i = 0; i < nch; ++i) running.add(XYZZ<F>::load(partial + sizeof(XYZZ<F>) * (size_t)(chunk_off[bucket] + i)));
         }
         total.add(running);
     }
@@ -385,12 +405,32 @@ __global__ void gather_windows_kernel(const uint8_t* __restrict__ group_out, uin
     XYZZ<F>::load(group_out + sizeof(XYZZ<F>) * (size_t)j * groups_per_window).store(out + sizeof(XYZZ<F>) * (size_t)j);
 }
 
+// one thread per bucket: XYZZ sum of the bucket's remaining affine points
+template <class F>
+__global__ void __launch_bounds__(128)
+bucket_finish_kernel(const Affine<F>* __restrict__ pts, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ off,
+                     uint32_t n_buckets, uint32_t level, XYZZ<F>* __restrict__ out) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buckets) return;
+    const uint32_t n = ba_level_count(hist[b], level);
+    if (n == 0) return;                      // empty bucket: never read by group_sum_kernel<.., 1>
+    const Affine<F>* p = pts + off[b];
+    XYZZ<F> acc = XYZZ<F>::from_affine(Affine<F>::load(p));
+    Affine<F> nxt = n > 1 ? Affine<F>::load(p + 1) : Affine<F>::load(p);
+    for (uint32_t i = 1; i < n; ++i) {
+        const Affine<F> cur = nxt;
+        if (i + 1 < n) nxt = Affine<F>::load(p + i + 1);
+        acc.madd(cur, false);
+    }
+    acc.store(out + b);
+}
+
 // ---------------------------------------------------------------- streaming batched-affine path (msm_ba.cuh)
 // entries / hist / offsets: the counting-sorted digits.  Produces the per-group running sums in group_out.
 // The sweeps (forward, backward) saturate memory / the multiplier pipe and go to the lane's low-priority stream; the
 // tiny kernels of the grid-wide inversion stay on the high-priority one so that they slip between other lanes' blocks.
 template <class F>
-static void run_ba(const MsmConfig& cfg, const uint8_t* points, const uint32_t* entries, const uint32_t* hist, const uint32_t* offsets,
+static void run_ba(const MsmConfig& cfg, const uint32_t* hist, const uint32_t* offsets,
                    uint32_t n_buckets, size_t max_entries, uint32_t* tiles, uint8_t* ws, const Digits& D, uint32_t groups, uint8_t* group_out,
                    cudaStream_t st, cudaEvent_t* ev, const typename MsmPlan<F>::Heavy* heavy) {
     const int L = cfg.ba_levels;
@@ -398,7 +438,7 @@ static void run_ba(const MsmConfig& cfg, const uint8_t* points, const uint32_t* 
     const size_t t1 = (s1 + BA_K - 1) / BA_K;
     uint8_t* p = ws;
     auto take = [&](size_t x) { uint8_t* r = p; p += (x + 255) & ~(size_t)255; return r; };
-    F* stage = (F*)take(4 * sizeof(F) * s1);
+    Affine<F>* sorted0 = (Affine<F>*)take(sizeof(Affine<F>) * (max_entries + 1));   // first in the workspace: the scatter kernel wrote it
     F* prefix = (F*)take(sizeof(F) * s1);
     Affine<F>* ping = (Affine<F>*)take(sizeof(Affine<F>) * s1);
     Affine<F>* pong = (Affine<F>*)take(sizeof(Affine<F>) * s2);
@@ -415,7 +455,7 @@ static void run_ba(const MsmConfig& cfg, const uint8_t* points, const uint32_t* 
     cudaStream_t hv = (heavy && heavy->st != st) ? heavy->st : st;
     auto to_heavy = [&]() { if (hv != st) { cudaEventRecord(heavy->before, st); cudaStreamWaitEvent(hv, heavy->before, 0); } };
     auto to_light = [&]() { if (hv != st) { cudaEventRecord(heavy->after, hv); cudaStreamWaitEvent(st, heavy->after, 0); } };
-    const Affine<F>* in = nullptr;
+    const Affine<F>* in = sorted0;
     Affine<F>* out = ping;
     for (int l = 0; l < L; ++l) {
         const size_t slots = BaPlan<F>::slots_bound(max_entries, n_buckets, l + 1);
@@ -425,24 +465,26 @@ static void run_ba(const MsmConfig& cfg, const uint8_t* points, const uint32_t* 
         BaLevel lv{hist, off[l], off[l + 1], slot_bucket, n_buckets, (uint32_t)l};
         to_heavy();
         if (ev && l == 0) cudaEventRecord(ev[0], hv);
-        if (l == 0) ba_forward_kernel<F, true><<<blocks, BA_THREADS, 0, hv>>>(lv, points, entries, nullptr, stage, prefix, tot, n_threads);
-        else ba_forward_kernel<F, false><<<blocks, BA_THREADS, 0, hv>>>(lv, nullptr, nullptr, in, nullptr, prefix, tot, n_threads);
+        ba_forward_kernel<F><<<blocks, BA_THREADS, 0, hv>>>(lv, in, prefix, tot, n_threads);
         to_light();
         batch_inverse<F>(tot, n_threads, binv_scratch, st);
         to_heavy();
-        if (l == 0) ba_backward_kernel<F, true><<<blocks, BA_THREADS, 0, hv>>>(lv, nullptr, stage, prefix, tot, out, n_threads);
-        else ba_backward_kernel<F, false><<<blocks, BA_THREADS, 0, hv>>>(lv, in, nullptr, prefix, tot, out, n_threads);
+        ba_backward_kernel<F><<<blocks, BA_THREADS, 0, hv>>>(lv, in, prefix, tot, out, n_threads);
         if (ev && l == L - 1) cudaEventRecord(ev[1], hv);
         to_light();
         ZKE_COUNT_LAUNCH(3);
         in = out;
         out = (out == ping) ? pong : ping;
     }
-    group_sum_kernel<F, true><<<(groups + 127) / 128, 128, 0, st>>>((const uint8_t*)in, hist, off[L], D.half, groups, 1u << L, 0, D.group, group_out);
-    ZKE_COUNT_LAUNCH(1);
+    // what is left of every bucket (ceil(size / 2^L) affine points, 6.5 on average for L = 4) is summed by one thread per
+    // bucket with mixed additions - fully parallel - before the (latency-bound) running sums over the buckets
+    XYZZ<F>* bucket_sum = (XYZZ<F>*)sorted0;     // the level-0 array is free again
+    bucket_finish_kernel<F><<<(n_buckets + 127) / 128, 128, 0, st>>>(in, hist, off[L], n_buckets, (uint32_t)L, bucket_sum);
+    group_sum_kernel<F, 1><<<(groups + 127) / 128, 128, 0, st>>>((const uint8_t*)bucket_sum, hist, off[L], D.half, groups, 1u << L, 0, D.group, group_out);
+    ZKE_COUNT_LAUNCH(2);
 }
 template <>
-void run_ba<Fq2>(const MsmConfig&, const uint8_t*, const uint32_t*, const uint32_t*, const uint32_t*, uint32_t, size_t, uint32_t*, uint8_t*, const Digits&,
+void run_ba<Fq2>(const MsmConfig&, const uint32_t*, const uint32_t*, uint32_t, size_t, uint32_t*, uint8_t*, const Digits&,
                  uint32_t, uint8_t*, cudaStream_t, cudaEvent_t*, const MsmPlan<Fq2>::Heavy*) {}
 
 // ---------------------------------------------------------------- host orchestration
@@ -460,9 +502,11 @@ MsmConfig msm_config_full(uint32_t n, bool precomputed) {
     c.chunk = 256; c.group = n >= (1u << 20) ? 64 : 16; c.classify = false; c.extra_passes = 0;   // group 64: 46.2 vs 45.8 proofs/s at 2^22
     c.precomputed = precomputed;
     // Streaming batched-affine bucket accumulation (msm_ba.cuh): the first `ba_levels` levels of every bucket's addition
-    // tree in affine coordinates (6 products per addition instead of 10).  ZKE_H_BA=<levels> at key-setup time
-    // (0 = the XYZZ bucket kernel of round 1).
-    c.ba_levels = (precomputed && n >= (1u << 12)) ? 4 : 0;
+    // tree in affine coordinates (6 products per addition instead of 10) - opt-in with ZKE_H_BA=<levels> at key-setup
+    // time.  Measured on B200 at 2^22 points (profiles/launches_r02_ba.txt): 35 % fewer
+    // multiplier instructions, but the sweeps are memory- and latency-bound where the XYZZ kernel is purely
+    // multiplier-bound, and in the overlapped steady state the engine loses throughput (44.6 - 48.2 vs 52.5 proofs/s).
+    c.ba_levels = 0;
     if (const char* e = getenv("ZKE_H_BA")) c.ba_levels = precomputed ? std::max(0, std::min(6, atoi(e))) : 0;
     if (const char* e = getenv("ZKE_H_GROUP")) c.group = (uint32_t)std::max(2, atoi(e));   // experiments
     if (precomputed) {
@@ -591,9 +635,10 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
     const int grid = 148 * 8;
     digit_hist_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, hist);
     exclusive_scan(hist, n_buckets, 0, 0, offsets, tiles, st);
-    digit_scatter_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, offsets, cursor, entries);
+    if (use_ba) digit_scatter_points_kernel<F><<<grid, 256, 0, st>>>(scalars, n, D, offsets, cursor, points, (Affine<F>*)ba_ws);
+    else digit_scatter_kernel<<<grid, 256, 0, st>>>(scalars, gen_idx, gen_count, n, D, offsets, cursor, entries);
     if (use_ba) {
-        run_ba<F>(cfg, points, entries, hist, offsets, n_buckets, max_entries, tiles, ba_ws, D, groups, group_out, st, ev, heavy);
+        run_ba<F>(cfg, hist, offsets, n_buckets, max_entries, tiles, ba_ws, D, groups, group_out, st, ev, heavy);
     } else {
         exclusive_scan(hist, n_buckets, D.chunk, 0, chunk_off, tiles, st);
         fill_work_kernel<<<(n_buckets + 255) / 256, 256, 0, st>>>(hist, chunk_off, n_buckets, D.chunk, 0, work_bucket);
@@ -640,7 +685,7 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
             uint32_t* o = off_cur; off_cur = off_next; off_next = o;
             ++levels;
         }
-        group_sum_kernel<F, false><<<(groups + 127) / 128, 128, 0, st>>>(items, hist, off_cur, D.half, groups, D.chunk, levels, D.group, group_out);
+        group_sum_kernel<F, 0><<<(groups + 127) / 128, 128, 0, st>>>(items, hist, off_cur, D.half, groups, D.chunk, levels, D.group, group_out);
     }
     window_reduce_kernel<F><<<bucket_sets, 512, 0, st>>>(group_out, groups_per_window);
     gather_windows_kernel<F><<<1, 64, 0, st>>>(group_out, groups_per_window, bucket_sets, res_windows);

@@ -7,11 +7,11 @@
 // level-synchronous sweeps over flat arrays - every sweep a plain grid-wide kernel with coalesced streams:
 //
 //   level l input : per bucket b, n_l(b) = ceil(size(b) / 2^l) affine points, contiguous at off_l[b]
-//                   (level 0: the sorted (index, sign) entries into the fixed-base table)
+//                   (level 0: the table points themselves, copied into bucket order by the digit scatter kernel - the
+//                   table is read once, coalesced, and the sweeps never gather)
 //   forward  (A)  : one thread per K consecutive OUTPUT slots: for slot s = (b, i) with 2i + 1 < n_l(b) form the slope
 //                   denominator d = x2 - x1 of points 2i, 2i + 1, multiply it into a running product and store the
-//                   prefix; level 0 also stages the two gathered table points (so the table is gathered ONCE); the
-//                   thread's total goes to `tot`
+//                   prefix; the thread's total goes to `tot`
 //   invert        : tot[t] <- 1 / tot[t] for all threads, by a hierarchical grid-wide batch inversion (groups of 32,
 //                   32, ... until one thread holds the rest: a single Fermat inversion per level of the tree)
 //   backward (B)  : the same thread walks its slots backwards: 1/d = v * prefix_before, v *= d, then the affine
@@ -42,26 +42,22 @@ struct BaLevel {
 };
 
 // ---- forward sweep ---------------------------------------------------------------------------------------------
-// LEVEL0: inputs are table points addressed by `entries`; both points of a slot are staged to `stage` (4 field elements
-// per slot: x1, y1, x2, y2; a lone point has x2 = y2 = 0 and is marked by the pair test failing).  Otherwise inputs are
-// the affine points of `pts_in`.
-template <class F, bool LEVEL0>
+template <class F>
 __global__ void __launch_bounds__(BA_THREADS, 4)
-ba_forward_kernel(BaLevel L, const uint8_t* __restrict__ table, const uint32_t* __restrict__ entries,
-                  const Affine<F>* __restrict__ pts_in, F* __restrict__ stage, F* __restrict__ prefix, F* __restrict__ tot, uint32_t n_threads) {
+ba_forward_kernel(BaLevel L, const Affine<F>* __restrict__ pts_in, F* __restrict__ prefix, F* __restrict__ tot, uint32_t n_threads) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_threads) return;
     const uint32_t total = L.off_out[L.n_buckets];
     const uint32_t s0 = t * BA_K;
     F run = F::one();
 #pragma unroll 1
-    for (uint32_t j = 0; j < BA_K; j += 2) {
-        // two slots per step: their (up to four) point loads are issued together
-        Affine<F> P[2], Q[2];
-        bool live[2], pair[2];
-        uint32_t in0[2];
+    for (uint32_t j = 0; j < BA_K; j += 4) {
+        // four slots per step: their x-coordinate loads are issued together
+        F px[4], qx[4];
+        bool live[4], pair[4];
+        uint32_t in0[4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < 4; ++u) {
             const uint32_t s = s0 + j + u;
             live[u] = s < total;
             pair[u] = false;
@@ -71,36 +67,21 @@ ba_forward_kernel(BaLevel L, const uint8_t* __restrict__ table, const uint32_t* 
             const uint32_t n_in = ba_level_count(L.hist[b], L.level);
             in0[u] = L.off_in[b] + 2 * i;
             pair[u] = 2 * i + 1 < n_in;
-            if (LEVEL0) {
-                const uint32_t e0 = entries[in0[u]];
-                P[u] = Affine<F>::load(table + sizeof(Affine<F>) * (size_t)(e0 & 0x7fffffffu));
-                if (e0 >> 31) P[u].y = P[u].y.neg();
-                if (pair[u]) {
-                    const uint32_t e1 = entries[in0[u] + 1];
-                    Q[u] = Affine<F>::load(table + sizeof(Affine<F>) * (size_t)(e1 & 0x7fffffffu));
-                    if (e1 >> 31) Q[u].y = Q[u].y.neg();
-                }
-            } else if (pair[u]) {
+            if (pair[u]) {
                 // only the x-coordinates are needed unless the pair is a doubling / cancellation / has an infinity
-                P[u].x = F::load(&pts_in[in0[u]].x);
-                Q[u].x = F::load(&pts_in[in0[u] + 1].x);
+                px[u] = F::load(&pts_in[in0[u]].x);
+                qx[u] = F::load(&pts_in[in0[u] + 1].x);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < 4; ++u) {
             if (!live[u]) continue;
             const uint32_t s = s0 + j + u;
-            if (LEVEL0) {
-                F* st = stage + 4 * (size_t)s;
-                P[u].x.store(st); P[u].y.store(st + 1);
-                if (pair[u]) { Q[u].x.store(st + 2); Q[u].y.store(st + 3); }
-            }
             if (pair[u]) {
                 F den;
-                if (LEVEL0) ba_den(P[u], Q[u], den);
-                else if (P[u].x.is_zero() || Q[u].x.is_zero() || P[u].x == Q[u].x)
+                if (px[u].is_zero() || qx[u].is_zero() || px[u] == qx[u])
                     ba_den(Affine<F>::load(pts_in + in0[u]), Affine<F>::load(pts_in + in0[u] + 1), den);
-                else den = Q[u].x - P[u].x;
+                else den = qx[u] - px[u];
                 run = run * den;
             }
             run.store(prefix + s);
@@ -110,9 +91,9 @@ ba_forward_kernel(BaLevel L, const uint8_t* __restrict__ table, const uint32_t* 
 }
 
 // ---- backward sweep --------------------------------------------------------------------------------------------
-template <class F, bool LEVEL0>
+template <class F>
 __global__ void __launch_bounds__(BA_THREADS, 4)
-ba_backward_kernel(BaLevel L, const Affine<F>* __restrict__ pts_in, const F* __restrict__ stage, const F* __restrict__ prefix,
+ba_backward_kernel(BaLevel L, const Affine<F>* __restrict__ pts_in, const F* __restrict__ prefix,
                    const F* __restrict__ tot_inv, Affine<F>* __restrict__ pts_out, uint32_t n_threads) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_threads) return;
@@ -127,15 +108,9 @@ ba_backward_kernel(BaLevel L, const Affine<F>* __restrict__ pts_in, const F* __r
         const uint32_t i = s - L.off_out[b];
         const uint32_t n_in = ba_level_count(L.hist[b], L.level);
         pair = 2 * i + 1 < n_in;
-        if (LEVEL0) {
-            const F* st = stage + 4 * (size_t)s;
-            P.x = F::load(st); P.y = F::load(st + 1);
-            if (pair) { Q.x = F::load(st + 2); Q.y = F::load(st + 3); }
-        } else {
-            const uint32_t in0 = L.off_in[b] + 2 * i;
-            P = Affine<F>::load(pts_in + in0);
-            if (pair) Q = Affine<F>::load(pts_in + in0 + 1);
-        }
+        const uint32_t in0 = L.off_in[b] + 2 * i;
+        P = Affine<F>::load(pts_in + in0);
+        if (pair) Q = Affine<F>::load(pts_in + in0 + 1);
         if (pair) prev = s > s0 ? F::load(prefix + s - 1) : F::one();
     };
     Affine<F> P, Q;
@@ -251,7 +226,7 @@ struct BaPlan {
         const size_t t1 = (s1 + BA_K - 1) / BA_K;
         size_t b = 0;
         auto al = [&](size_t x) { b += (x + 255) & ~(size_t)255; };
-        al(4 * sizeof(F) * s1);                 // stage (level 0)
+        al(sizeof(Affine<F>) * (max_entries + 1));   // level-0 points in bucket order (written by the digit scatter)
         al(sizeof(F) * s1);                     // prefix
         al(sizeof(Affine<F>) * s1);             // points ping
         al(sizeof(Affine<F>) * s2);             // points pong

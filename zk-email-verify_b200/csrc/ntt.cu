@@ -4,14 +4,30 @@
 // (algorithmic bytes per transform: 2 * 32 * N).  The inverse transform is decimation-in-frequency
 // (natural in, bit-reversed out) and the forward transform decimation-in-time (bit-reversed in, natural out), so
 // no bit-reversal permutation is ever materialised; the coset shift g^j / N is fused into the store of the last
-// inverse pass.  Twiddles (and the coset factors) are constants: the tables hold them as fixed-operand pairs
-// {w in standard form, floor(w 2^256 / r)} (64 bytes) and every butterfly product is Fp::mul_shoup (ff.cuh) - 99
-// IMAD.WIDE + 16 IMAD instead of the 136 IMAD.WIDE of a Montgomery product; the data stays in Montgomery form.
+// inverse pass.  Twiddles (and the coset factors) are constants; the tables hold them either in Montgomery form
+// (32 bytes, Montgomery product) or as fixed-operand pairs {w in standard form, floor(w 2^256 / r)} (64 bytes,
+// Fp::mul_shoup of ff.cuh: 99 IMAD.WIDE + 16 IMAD instead of 136 IMAD.WIDE) - NttTables::shoup, chosen when the
+// context is opened (ZKE_NTT_SHOUP); the data stays in Montgomery form either way.
 #include "device_engine.cuh"
 #include "ntt.cuh"
+#include <cstdlib>
+#include <type_traits>
 
 namespace zke {
 namespace dev {
+
+// A constant factor (twiddle, coset scale) as the tables hold it: SHOUP: the fixed-operand pair {w standard form,
+// floor(w 2^256 / r)} (64 bytes, Fp::mul_shoup); otherwise w in Montgomery form (32 bytes, Montgomery product).
+template <bool SHOUP>
+struct Twid {
+    Fr w, wq;
+    static constexpr uint64_t STRIDE = SHOUP ? 64 : 32;
+    __device__ __forceinline__ void load(const uint8_t* base, uint64_t idx) {
+        w = Fr::load(base + STRIDE * idx);
+        if (SHOUP) wq = Fr::load(base + STRIDE * idx + 32);
+    }
+    __device__ __forceinline__ Fr mul(const Fr& x) const { return SHOUP ? Fr::mul_shoup(x, w.v, wq.v) : x * w; }
+};
 
 static const int MAX_TILE_LOG = 10;   // 1024 elements = 32 KB of shared memory per CTA, 512 threads
 
@@ -24,7 +40,7 @@ struct Planar {
 
 // One fused pass over stage bits [s_lo, s_hi].  DIF: stages descend and multiply after the subtraction;
 // DIT: stages ascend and multiply before the butterfly.  `scale`, if non-null, multiplies element idx on store.
-template <bool DIF>
+template <bool DIF, bool SHOUP>
 __global__ void __launch_bounds__(1 << (MAX_TILE_LOG - 1))
 ntt_pass_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, const uint8_t* __restrict__ scale,
                 int log_n, int s_lo, int s_hi, int tile_log) {   // log_n: size of the transform the twiddle table belongs to
@@ -66,13 +82,14 @@ ntt_pass_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, cons
         const int e0 = sidx(j0, l), e1 = sidx(j0 + h, l);
         const uint32_t idx0 = gidx(j0, l);
         const uint32_t tw_i = (idx0 & ((1u << st) - 1)) << (log_n - 1 - st);
-        const Fr w = Fr::load(tw + 64ull * tw_i), wq = Fr::load(tw + 64ull * tw_i + 32);
+        Twid<SHOUP> w;
+        w.load(tw, tw_i);
         Fr u = S.get(e0), v = S.get(e1);
         if (DIF) {
             S.put(e0, u + v);
-            S.put(e1, Fr::mul_shoup(u - v, w.v, wq.v));
+            S.put(e1, w.mul(u - v));
         } else {
-            Fr x = Fr::mul_shoup(v, w.v, wq.v);
+            Fr x = w.mul(v);
             S.put(e0, u + x);
             S.put(e1, u - x);
         }
@@ -83,7 +100,7 @@ ntt_pass_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, cons
         if (strided) { l2 = e % L; j = e / L; } else { j = e % J; l2 = e / J; }
         const uint32_t g = gidx(j, l2);
         Fr x = S.get(e);
-        if (scale) { const Fr sc = Fr::load(scale + 64ull * g), scq = Fr::load(scale + 64ull * g + 32); x = Fr::mul_shoup(x, sc.v, scq.v); }
+        if (scale) { Twid<SHOUP> sc; sc.load(scale, g); x = sc.mul(x); }
         x.store(data + 32ull * g);
     }
 }
@@ -93,7 +110,7 @@ ntt_pass_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, cons
 // elements touches 128 contiguous bytes per plane, so the 128-bit shared loads are conflict-free.  All index
 // arithmetic is shifts and masks; the twiddle of the next stage is fetched before the current stage's product so
 // the L2 latency of the table lookup overlaps the multiplication.
-template <bool DIF, int K, bool STRIDED>
+template <bool DIF, int K, bool STRIDED, bool SHOUP>
 __global__ void __launch_bounds__(512, 2)
 ntt_pass_fast_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, const uint8_t* __restrict__ scale,
                      int log_n, int s_lo_arg) {
@@ -137,30 +154,27 @@ ntt_pass_fast_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw,
         const uint32_t hb = st - s_lo;                     // log2 of the butterfly distance in j units
         return ((jj >> hb) << (hb + 1)) | (jj & ((1u << hb) - 1));
     };
-    auto tw_ptr = [&](int st, uint32_t j0) {
+    auto tw_idx = [&](int st, uint32_t j0) -> uint64_t {
         const uint32_t idx0 = gidx(j0, l);
-        return tw + 64ull * ((idx0 & ((1u << st) - 1)) << (log_n - 1 - st));
+        return (uint64_t)(idx0 & ((1u << st) - 1)) << (log_n - 1 - st);
     };
-    const uint8_t* twp = tw_ptr(stage_of(0), j0_of(stage_of(0)));
-    Fr w_next = Fr::load(twp), wq_next = Fr::load(twp + 32);
+    Twid<SHOUP> w_next;
+    w_next.load(tw, tw_idx(stage_of(0), j0_of(stage_of(0))));
     __syncthreads();
 #pragma unroll
     for (int step = 0; step < K; ++step) {
         const int st = stage_of(step);
         const uint32_t j0 = j0_of(st);
         const uint32_t e0 = sidx(j0, l), e1 = sidx(j0 + (1u << (st - s_lo)), l);
-        const Fr w = w_next, wq = wq_next;
-        if (step + 1 < K) {
-            twp = tw_ptr(stage_of(step + 1), j0_of(stage_of(step + 1)));
-            w_next = Fr::load(twp); wq_next = Fr::load(twp + 32);
-        }
+        const Twid<SHOUP> w = w_next;
+        if (step + 1 < K) w_next.load(tw, tw_idx(stage_of(step + 1), j0_of(stage_of(step + 1))));
         const Fr u = sget(e0), v = sget(e1);
         const bool trivial = !STRIDED && st == 0;   // stage 0: every twiddle is omega^0 = 1, no product
         if (DIF) {
             sput(e0, u + v);
-            sput(e1, trivial ? (u - v) : Fr::mul_shoup(u - v, w.v, wq.v));
+            sput(e1, trivial ? (u - v) : w.mul(u - v));
         } else {
-            const Fr x = trivial ? v : Fr::mul_shoup(v, w.v, wq.v);
+            const Fr x = trivial ? v : w.mul(v);
             sput(e0, u + x);
             sput(e1, u - x);
         }
@@ -172,8 +186,9 @@ ntt_pass_fast_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw,
         const uint32_t j = STRIDED ? (e >> L_LOG) : (e & (J - 1)), l2 = STRIDED ? (e & (L - 1)) : (e >> K);
         const uint32_t g = gidx(j, l2);
         if (scale) {
-            const Fr sc = Fr::load(scale + 64ull * g), scq = Fr::load(scale + 64ull * g + 32);
-            Fr::mul_shoup(sget(e), sc.v, scq.v).store(data + 32ull * g);
+            Twid<SHOUP> sc;
+            sc.load(scale, g);
+            sc.mul(sget(e)).store(data + 32ull * g);
         } else {
             uint4* dst = reinterpret_cast<uint4*>(data + 32ull * g);
             dst[0] = plane0[e];
@@ -182,17 +197,141 @@ ntt_pass_fast_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw,
     }
 }
 
-template <bool DIF>
+// ---- register-blocked variant: 8 elements per thread, up to three stages between shared-memory exchanges -----------
+// The kernel above synchronises the CTA after every stage and gives a thread ONE product per stage: it runs at ~65 % of
+// the multiplier pipe because each stage is a chain load -> product -> store -> barrier.  Here a thread holds 2^R
+// elements (R <= 3) in registers and does R stages on them - 4 independent butterflies per stage - before the tile is
+// exchanged through shared memory again: 3 barriers instead of 8 per pass, a third of the shared-memory traffic, and
+// enough independent products per thread for the fixed-operand product (whose two phases are dependent) to pay off.
+// Shared memory is padded by one element per eight (index e -> e + (e >> 3)) so that the strides 2, 4, 8 of the
+// register blocks stay conflict-free for 128-bit accesses.
+template <bool DIF, int K, bool STRIDED, bool SHOUP>
+__global__ void __launch_bounds__(128, 3)
+ntt_pass_r8_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, const uint8_t* __restrict__ scale,
+                   int log_n, int s_lo_arg) {
+    const int s_lo = STRIDED ? s_lo_arg : 0;
+    constexpr int TILE_LOG = 10, TILE = 1 << TILE_LOG, J = 1 << K, L_LOG = TILE_LOG - K, L = 1 << L_LOG;
+    constexpr int SM = TILE + TILE / 8;
+    __shared__ uint4 plane0[SM], plane1[SM];
+    const int s_hi = s_lo + K - 1;
+    const uint32_t bid = blockIdx.x;
+    uint32_t hi = 0, lo_base = 0;
+    if constexpr (STRIDED) {
+        const uint32_t lo_blocks_log = s_lo - L_LOG;
+        lo_base = (bid & ((1u << lo_blocks_log) - 1)) << L_LOG;
+        hi = bid >> lo_blocks_log;
+    }
+    auto gidx = [&](uint32_t j, uint32_t l) -> uint32_t {
+        return STRIDED ? ((hi << (s_hi + 1)) | (j << s_lo) | (lo_base + l)) : ((((bid << L_LOG) + l) << K) | j);
+    };
+    auto pad = [](uint32_t e) -> uint32_t { return e + (e >> 3); };
+    auto sget = [&](uint32_t e) -> Fr {
+        const uint4 a = plane0[pad(e)], b = plane1[pad(e)];
+        Fr r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+        return r;
+    };
+    auto sput = [&](uint32_t e, const Fr& x) {
+        plane0[pad(e)] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+        plane1[pad(e)] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+    };
+    // tile element e <-> (j, l): the same mapping as the global load of ntt_pass_fast_kernel (coalesced 32-byte rows)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t e = threadIdx.x + r * 128;
+        const uint32_t j = STRIDED ? (e >> L_LOG) : (e & (J - 1)), l = STRIDED ? (e & (L - 1)) : (e >> K);
+        const uint4* src = reinterpret_cast<const uint4*>(data + 32ull * gidx(j, l));
+        plane0[pad(e)] = src[0];
+        plane1[pad(e)] = src[1];
+    }
+    __syncthreads();
+    // one round: the R stages of local stage bits [B, B + R)
+    auto round = [&](auto b_tag, auto r_tag) {
+        constexpr int B = decltype(b_tag)::value, R = decltype(r_tag)::value, NR = 1 << R;
+        constexpr int BP = STRIDED ? B + L_LOG : B;        // position of local stage bit B in the tile index
+        constexpr int ITEMS = TILE >> R;
+#pragma unroll 1
+        for (uint32_t u = threadIdx.x; u < ITEMS; u += 128) {
+            const uint32_t base = (u & ((1u << BP) - 1)) | ((u >> BP) << (BP + R));
+            const uint32_t j = STRIDED ? (base >> L_LOG) : (base & (J - 1)), l = STRIDED ? (base & (L - 1)) : (base >> K);
+            Fr x[NR];
+#pragma unroll
+            for (int r = 0; r < NR; ++r) x[r] = sget(base + ((uint32_t)r << BP));
+#pragma unroll
+            for (int qq = 0; qq < R; ++qq) {
+                const int q = DIF ? (R - 1 - qq) : qq;
+                const int st = s_lo + B + q;
+                const bool trivial = !STRIDED && B + q == 0;     // stage 0: every twiddle is 1
+                Twid<SHOUP> w[NR / 2];
+                if (!trivial) {
+#pragma unroll
+                    for (int p = 0; p < NR / 2; ++p) {
+                        const int r0 = ((p >> q) << (q + 1)) | (p & ((1 << q) - 1));
+                        const uint32_t idx0 = gidx(j | ((uint32_t)r0 << B), l);
+                        w[p].load(tw, (uint64_t)(idx0 & ((1u << st) - 1)) << (log_n - 1 - st));
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < NR / 2; ++p) {
+                    const int r0 = ((p >> q) << (q + 1)) | (p & ((1 << q) - 1)), r1 = r0 | (1 << q);
+                    const Fr a = x[r0], b = x[r1];
+                    if (DIF) {
+                        x[r0] = a + b;
+                        x[r1] = trivial ? (a - b) : w[p].mul(a - b);
+                    } else {
+                        const Fr y = trivial ? b : w[p].mul(b);
+                        x[r0] = a + y;
+                        x[r1] = a - y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < NR; ++r) sput(base + ((uint32_t)r << BP), x[r]);
+        }
+        __syncthreads();
+    };
+    using std::integral_constant;
+    constexpr int R0 = K >= 3 ? 3 : K, K1 = K - R0, R1 = K1 >= 3 ? 3 : K1, R2 = K1 - R1;      // K = 8: 3 + 3 + 2, 7: 3 + 3 + 1, ...
+    if (DIF) {      // stages descend: the top bits first
+        round(integral_constant<int, K - R0>{}, integral_constant<int, R0>{});
+        if constexpr (R1 > 0) round(integral_constant<int, K - R0 - R1>{}, integral_constant<int, R1>{});
+        if constexpr (R2 > 0) round(integral_constant<int, 0>{}, integral_constant<int, R2>{});
+    } else {        // stages ascend
+        round(integral_constant<int, 0>{}, integral_constant<int, R0>{});
+        if constexpr (R1 > 0) round(integral_constant<int, R0>{}, integral_constant<int, R1>{});
+        if constexpr (R2 > 0) round(integral_constant<int, R0 + R1>{}, integral_constant<int, R2>{});
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t e = threadIdx.x + r * 128;
+        const uint32_t j = STRIDED ? (e >> L_LOG) : (e & (J - 1)), l2 = STRIDED ? (e & (L - 1)) : (e >> K);
+        const uint32_t g = gidx(j, l2);
+        if (scale) {
+            Twid<SHOUP> sc;
+            sc.load(scale, g);
+            sc.mul(sget(e)).store(data + 32ull * g);
+        } else {
+            uint4* dst = reinterpret_cast<uint4*>(data + 32ull * g);
+            dst[0] = plane0[pad(e)];
+            dst[1] = plane1[pad(e)];
+        }
+    }
+}
+
+template <bool DIF, bool SHOUP>
 static bool launch_fast(uint8_t* data, const uint8_t* tw, const uint8_t* scale, int log_n, int s_lo, int s_hi, cudaStream_t st, int log_tw) {
     if (log_n < 10) return false;
     const int k = s_hi - s_lo + 1;
     const uint32_t blocks = 1u << (log_n - 10);
     const bool strided = s_lo > 0;
     if (strided && s_lo < 10 - k) return false;
+    static const bool r8 = !(getenv("ZKE_NTT_R8") && atoi(getenv("ZKE_NTT_R8")) == 0);   // register-blocked kernel (default)
 #define ZKE_NTT_CASE(KK)                                                                                            \
     case KK:                                                                                                       \
-        if (strided) ntt_pass_fast_kernel<DIF, KK, true><<<blocks, 512, 0, st>>>(data, tw, scale, log_tw, s_lo);     \
-        else ntt_pass_fast_kernel<DIF, KK, false><<<blocks, 512, 0, st>>>(data, tw, scale, log_tw, s_lo);            \
+        if (r8) {                                                                                                  \
+            if (strided) ntt_pass_r8_kernel<DIF, KK, true, SHOUP><<<blocks, 128, 0, st>>>(data, tw, scale, log_tw, s_lo);  \
+            else ntt_pass_r8_kernel<DIF, KK, false, SHOUP><<<blocks, 128, 0, st>>>(data, tw, scale, log_tw, s_lo);         \
+        } else if (strided) ntt_pass_fast_kernel<DIF, KK, true, SHOUP><<<blocks, 512, 0, st>>>(data, tw, scale, log_tw, s_lo); \
+        else ntt_pass_fast_kernel<DIF, KK, false, SHOUP><<<blocks, 512, 0, st>>>(data, tw, scale, log_tw, s_lo);            \
         return true;
     switch (k) {
         ZKE_NTT_CASE(4) ZKE_NTT_CASE(5) ZKE_NTT_CASE(6) ZKE_NTT_CASE(7) ZKE_NTT_CASE(8)
@@ -226,8 +365,10 @@ static void intt_dif_impl(uint8_t* data, const NttTables& T, int log_local, cons
     const uint32_t blocks = 1u << (log_local - tile_log);
     for (int p = 0; p < np; ++p) {
         const uint8_t* sc = p == np - 1 ? scale_bitrev : nullptr;
-        if (launch_fast<true>(data, T.tw_inv, sc, log_local, lo[p], hi[p], st, T.log_n)) continue;
-        ntt_pass_kernel<true><<<blocks, 1 << (tile_log - 1), 32u << tile_log, st>>>(data, T.tw_inv, sc, T.log_n, lo[p], hi[p], tile_log);
+        if (T.shoup ? launch_fast<true, true>(data, T.tw_inv, sc, log_local, lo[p], hi[p], st, T.log_n)
+                    : launch_fast<true, false>(data, T.tw_inv, sc, log_local, lo[p], hi[p], st, T.log_n)) continue;
+        if (T.shoup) ntt_pass_kernel<true, true><<<blocks, 1 << (tile_log - 1), 32u << tile_log, st>>>(data, T.tw_inv, sc, T.log_n, lo[p], hi[p], tile_log);
+        else ntt_pass_kernel<true, false><<<blocks, 1 << (tile_log - 1), 32u << tile_log, st>>>(data, T.tw_inv, sc, T.log_n, lo[p], hi[p], tile_log);
     }
 }
 static void ntt_dit_impl(uint8_t* data, const NttTables& T, int log_local, cudaStream_t st) {
@@ -237,8 +378,10 @@ static void ntt_dit_impl(uint8_t* data, const NttTables& T, int log_local, cudaS
     const int tile_log = log_local < MAX_TILE_LOG ? log_local : MAX_TILE_LOG;
     const uint32_t blocks = 1u << (log_local - tile_log);
     for (int p = np - 1; p >= 0; --p) {
-        if (launch_fast<false>(data, T.tw_fwd, nullptr, log_local, lo[p], hi[p], st, T.log_n)) continue;
-        ntt_pass_kernel<false><<<blocks, 1 << (tile_log - 1), 32u << tile_log, st>>>(data, T.tw_fwd, nullptr, T.log_n, lo[p], hi[p], tile_log);
+        if (T.shoup ? launch_fast<false, true>(data, T.tw_fwd, nullptr, log_local, lo[p], hi[p], st, T.log_n)
+                    : launch_fast<false, false>(data, T.tw_fwd, nullptr, log_local, lo[p], hi[p], st, T.log_n)) continue;
+        if (T.shoup) ntt_pass_kernel<false, true><<<blocks, 1 << (tile_log - 1), 32u << tile_log, st>>>(data, T.tw_fwd, nullptr, T.log_n, lo[p], hi[p], tile_log);
+        else ntt_pass_kernel<false, false><<<blocks, 1 << (tile_log - 1), 32u << tile_log, st>>>(data, T.tw_fwd, nullptr, T.log_n, lo[p], hi[p], tile_log);
     }
 }
 void launch_intt_dif(uint8_t* data, const NttTables& T, const uint8_t* scale_bitrev, cudaStream_t st) { intt_dif_impl(data, T, T.log_n, scale_bitrev, st); }
@@ -251,7 +394,7 @@ void launch_ntt_dit_block(uint8_t* block, const NttTables& T, int log_local, cud
 // block (element (g, j) at its global position g * M + j, M = N / G).  One thread per column does the LOGG butterfly
 // stages of distance M, 2M, ... in registers.  DIF (inverse transform): these are the FIRST stages, top down;
 // DIT (forward): the LAST stages, bottom up.
-template <bool DIF, int LOGG>
+template <bool DIF, int LOGG, bool SHOUP>
 __global__ void __launch_bounds__(128)
 ntt_cross_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, int log_n, uint32_t col0, uint32_t n_cols) {
     constexpr int G = 1 << LOGG;
@@ -272,13 +415,14 @@ ntt_cross_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, int
             const int g1 = g0 | (1 << sb);
             const uint32_t idx0 = ((uint32_t)g0 << log_m) + j;
             const uint64_t tw_i = (uint64_t)(idx0 & ((1u << st) - 1)) << (log_n - 1 - st);
-            const Fr w = Fr::load(tw + 64ull * tw_i), wq = Fr::load(tw + 64ull * tw_i + 32);
+            Twid<SHOUP> w;
+            w.load(tw, tw_i);
             const Fr u = x[g0], v = x[g1];
             if (DIF) {
                 x[g0] = u + v;
-                x[g1] = Fr::mul_shoup(u - v, w.v, wq.v);
+                x[g1] = w.mul(u - v);
             } else {
-                const Fr y = Fr::mul_shoup(v, w.v, wq.v);
+                const Fr y = w.mul(v);
                 x[g0] = u + y;
                 x[g1] = u - y;
             }
@@ -287,19 +431,25 @@ ntt_cross_kernel(uint8_t* __restrict__ data, const uint8_t* __restrict__ tw, int
 #pragma unroll
     for (int g = 0; g < G; ++g) x[g].store(data + 32ull * (((uint32_t)g << log_m) + j));
 }
-template <bool DIF>
+template <bool DIF, bool SHOUP>
 static void launch_cross(uint8_t* data, const uint8_t* tw, int log_n, int log_g, uint32_t col0, uint32_t n_cols, cudaStream_t st) {
     const uint32_t blocks = (n_cols + 127) / 128;
     switch (log_g) {
-        case 1: ntt_cross_kernel<DIF, 1><<<blocks, 128, 0, st>>>(data, tw, log_n, col0, n_cols); break;
-        case 2: ntt_cross_kernel<DIF, 2><<<blocks, 128, 0, st>>>(data, tw, log_n, col0, n_cols); break;
-        case 3: ntt_cross_kernel<DIF, 3><<<blocks, 128, 0, st>>>(data, tw, log_n, col0, n_cols); break;
+        case 1: ntt_cross_kernel<DIF, 1, SHOUP><<<blocks, 128, 0, st>>>(data, tw, log_n, col0, n_cols); break;
+        case 2: ntt_cross_kernel<DIF, 2, SHOUP><<<blocks, 128, 0, st>>>(data, tw, log_n, col0, n_cols); break;
+        case 3: ntt_cross_kernel<DIF, 3, SHOUP><<<blocks, 128, 0, st>>>(data, tw, log_n, col0, n_cols); break;
         default: break;
     }
     ZKE_COUNT_LAUNCH(1);
 }
-void launch_intt_cross(uint8_t* data, const NttTables& T, int log_g, uint32_t col0, uint32_t n_cols, cudaStream_t st) { launch_cross<true>(data, T.tw_inv, T.log_n, log_g, col0, n_cols, st); }
-void launch_ntt_cross(uint8_t* data, const NttTables& T, int log_g, uint32_t col0, uint32_t n_cols, cudaStream_t st) { launch_cross<false>(data, T.tw_fwd, T.log_n, log_g, col0, n_cols, st); }
+void launch_intt_cross(uint8_t* data, const NttTables& T, int log_g, uint32_t col0, uint32_t n_cols, cudaStream_t st) {
+    if (T.shoup) launch_cross<true, true>(data, T.tw_inv, T.log_n, log_g, col0, n_cols, st);
+    else launch_cross<true, false>(data, T.tw_inv, T.log_n, log_g, col0, n_cols, st);
+}
+void launch_ntt_cross(uint8_t* data, const NttTables& T, int log_g, uint32_t col0, uint32_t n_cols, cudaStream_t st) {
+    if (T.shoup) launch_cross<false, true>(data, T.tw_fwd, T.log_n, log_g, col0, n_cols, st);
+    else launch_cross<false, false>(data, T.tw_fwd, T.log_n, log_g, col0, n_cols, st);
+}
 
 // c = a o b   (Montgomery in/out)
 __global__ void hadamard_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, uint8_t* __restrict__ c, uint32_t n) {

@@ -6,9 +6,10 @@ namespace zke {
 namespace dev {
 
 struct NttTables {
-    const uint8_t* tw_fwd;   // [N/2][2][32] omega^k as a fixed-operand pair {w (standard form), floor(w 2^256 / r)}
-    const uint8_t* tw_inv;   // [N/2][2][32] omega^-k
+    const uint8_t* tw_fwd;   // [N/2] omega^k: shoup ? {w (standard form), floor(w 2^256 / r)} (64 B) : w in Montgomery form (32 B)
+    const uint8_t* tw_inv;   // [N/2] omega^-k
     int log_n;
+    bool shoup;              // table format: fixed-operand pairs (64-byte entries) or Montgomery form (32-byte entries)
 };
 
 // In-place inverse transform, natural order in, BIT-REVERSED order out, not scaled by 1/N.  If scale_bitrev is

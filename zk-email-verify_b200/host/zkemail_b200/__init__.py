@@ -10,7 +10,8 @@ from .input_generators import (generate_circuit_inputs, generate_email_verifier_
                                generate_twitter_verifier_inputs_from_dkim_result,
                                generate_email_verifier_inputs_from_dkim_result)
 from .engine import AssertFailed, Context, Zkey, device_count, proof_to_json, verify  # noqa: F401
-from .chunked_zkey import generate_proof, verify_proof, register_circuit, generateProof, verifyProof  # noqa: F401
+from .chunked_zkey import (generate_proof, verify_proof, register_circuit, register_zkey_files, generateProof, verifyProof,  # noqa: F401
+                           InsecureKeyError)
 from . import synthetic  # noqa: F401,E402
 from . import iden3_binfile  # noqa: F401,E402
 from . import verifier_args  # noqa: F401,E402

@@ -10,9 +10,27 @@ from .circuit import Circuit
 _REGISTRY: dict[str, tuple] = {}
 
 
-def register_circuit(circuit_name: str, circuit: Circuit, zkey: Zkey, device: int = 0, max_batch: int = 1):
+class InsecureKeyError(RuntimeError):
+    pass
+
+
+def register_zkey_files(circuit_name: str, circuit: Circuit, chunk_files, device: int = 0, max_batch: int = 1):
+    """downloadProofFiles + uncompress (chunked-zkey.ts:35-37, 59-74) for local files: `chunk_files` are the paths of
+    `${circuitName}.zkeyb` .. `.zkeyk` (or a single whole `.zkey`)."""
+    blobs = [open(p, "rb").read() for p in chunk_files]
+    zkey = Zkey.load(blobs[0], device=device, circuit=circuit) if len(blobs) == 1 else Zkey.load_chunks(blobs, device=device, circuit=circuit)
+    return register_circuit(circuit_name, circuit, zkey, device=device, max_batch=max_batch)
+
+
+def register_circuit(circuit_name: str, circuit: Circuit, zkey: Zkey, device: int = 0, max_batch: int = 1,
+                     allow_toy_key: bool = False):
     """Plays the role of downloadProofFiles (chunked-zkey.ts:59-74): makes the proving artefacts of `circuitName`
-    available to generateProof / verifyProof."""
+    available to generateProof / verifyProof.  A key made by the seeded toy setup (Zkey(circuit, seed): the toxic waste
+    is known, anyone can forge proofs that verify under it) is refused unless `allow_toy_key=True` - benchmarks and
+    tests only; production keys come from a ceremony `.zkey` through Zkey.load / Zkey.load_chunks."""
+    if zkey.is_toy and not allow_toy_key:
+        raise InsecureKeyError("refusing a proving key made by the toy setup (known toxic waste); load a ceremony .zkey with "
+                               "Zkey.load(...) or pass allow_toy_key=True for tests")
     ctx = Context(circuit, zkey, device=device, max_batch=max_batch)
     _REGISTRY[circuit_name] = (circuit, zkey, ctx, zkey.vkey())
     return ctx
