@@ -324,7 +324,10 @@ static bool launch_fast(uint8_t* data, const uint8_t* tw, const uint8_t* scale, 
     const uint32_t blocks = 1u << (log_n - 10);
     const bool strided = s_lo > 0;
     if (strided && s_lo < 10 - k) return false;
-    static const bool r8 = !(getenv("ZKE_NTT_R8") && atoi(getenv("ZKE_NTT_R8")) == 0);   // register-blocked kernel (default)
+    // ZKE_NTT_R8=1 selects the register-blocked kernel.  Measured on B200 (profiles/ntt_ab_r02.txt): it is faster alone
+    // (5.37 vs 5.59 ms for the six 2^22 transforms, Montgomery twiddles) but its 160 registers per thread leave less room
+    // for the blocks of other proofs' kernels, and the overlapped steady state is 1.8 % slower (53.1 vs 54.1 proofs/s).
+    static const bool r8 = getenv("ZKE_NTT_R8") && atoi(getenv("ZKE_NTT_R8")) != 0;
 #define ZKE_NTT_CASE(KK)                                                                                            \
     case KK:                                                                                                       \
         if (r8) {                                                                                                  \

@@ -6,6 +6,9 @@ import koffi from 'koffi';
 const lib = koffi.load(process.env.ZKEMAIL_B200_LIB ?? 'libzkemail_b200.so');
 const zke_circuit_build = lib.func('void* zke_circuit_build(const char*, const int64_t*, size_t, char*, size_t)');
 const zke_setup = lib.func('void* zke_setup(void*, uint64_t, int, char*, size_t)');
+const zke_zkey_load = lib.func('void* zke_zkey_load(const void*, size_t, int, char*, size_t)');
+const zke_zkey_load_chunks = lib.func('void* zke_zkey_load_chunks(const void**, const size_t*, size_t, int, char*, size_t)');
+const zke_zkey_is_toy = lib.func('int zke_zkey_is_toy(void*)');
 const zke_ctx_open = lib.func('void* zke_ctx_open(void*, void*, int, uint32_t, char*, size_t)');
 const zke_zkey_vkey_json = lib.func('int zke_zkey_vkey_json(void*, char*, size_t*)');
 const zke_fullprove_json = lib.func('int zke_fullprove_json(void*, void*, const char*, char*, size_t*, char*, size_t*, char*, size_t)');
@@ -15,13 +18,32 @@ const cstr = (b: Buffer) => b.toString('utf8', 0, b.indexOf(0));
 type Entry = { circuit: unknown; zkey: unknown; ctx: unknown };
 const registry = new Map<string, Entry>();
 
-/** Plays the role of downloadProofFiles (chunked-zkey.ts:59-74): makes `${circuitName}.zkey` resident on a GPU. */
-export function registerEmailVerifier(circuitName: string, params: number[], seed = 1, device = 0): void {
+/**
+ * Plays the role of downloadProofFiles + uncompress (chunked-zkey.ts:35-37, 59-74): makes `${circuitName}.zkey`
+ * resident on a GPU.  `zkeyChunks` are the contents of `${circuitName}.zkeyb` .. `.zkeyk` (the fork's per-section
+ * files, chunked-zkey.ts:9) or a single whole `.zkey`; they are parsed and validated by zke_zkey_load[_chunks].
+ * The circuit's witness program replaces `${circuitName}.wasm`.
+ */
+export function registerEmailVerifier(circuitName: string, params: number[], zkeyChunks: Buffer[], device = 0): void {
+  const err = Buffer.alloc(4096);
+  const circuit = zke_circuit_build('EmailVerifier', BigInt64Array.from(params.map(BigInt)), params.length, err, err.length);
+  if (!circuit) throw new Error(cstr(err));
+  const zkey = zkeyChunks.length === 1
+    ? zke_zkey_load(zkeyChunks[0], zkeyChunks[0].length, device, err, err.length)
+    : zke_zkey_load_chunks(zkeyChunks, BigUint64Array.from(zkeyChunks.map((c) => BigInt(c.length))), zkeyChunks.length, device, err, err.length);
+  if (!zkey) throw new Error(cstr(err));
+  const ctx = zke_ctx_open(circuit, zkey, device, 1, err, err.length);
+  if (!ctx) throw new Error(cstr(err));
+  registry.set(circuitName, { circuit, zkey, ctx });
+}
+
+/** Tests and benchmarks only: a key from the seeded TOY setup (known toxic waste - proofs under it are forgeable). */
+export function registerEmailVerifierWithToyKey(circuitName: string, params: number[], seed: number, device = 0): void {
   const err = Buffer.alloc(4096);
   const circuit = zke_circuit_build('EmailVerifier', BigInt64Array.from(params.map(BigInt)), params.length, err, err.length);
   if (!circuit) throw new Error(cstr(err));
   const zkey = zke_setup(circuit, BigInt(seed), device, err, err.length);
-  if (!zkey) throw new Error(cstr(err));
+  if (!zkey || zke_zkey_is_toy(zkey) !== 1) throw new Error(cstr(err));
   const ctx = zke_ctx_open(circuit, zkey, device, 1, err, err.length);
   if (!ctx) throw new Error(cstr(err));
   registry.set(circuitName, { circuit, zkey, ctx });
