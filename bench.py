@@ -363,6 +363,17 @@ def main():
                                           "witness_kernel_ms_per_batch": prof["witness"]["ms"] / max(1, prof["witness"]["count"])},
                  "single_email_fullprove_latency_ms": {"median": 1e3 * lat[len(lat) // 2], "min": 1e3 * lat[0],
                                                        "what": "zke_fullprove(batch = 1) with host buffers, wall clock"}}
+    cpu_baseline = None
+    if rank == 0 and not args.skip_cpu_baseline:
+        dt, proof_cpu, _ = cpu_reference_proof(z, circuit, zk, packed_list[0], host_threads, rs=(12345, 67890))
+        # same email, same (r, s) on the GPU: full-size bit-exact parity check on the side
+        rs = (12345).to_bytes(32, "little") + (67890).to_bytes(32, "little")
+        ctx.witness(packed_list[0], 1, want_witness=False)
+        proofs_gpu, _, _ = ctx.prove(1, rs)
+        cpu_baseline = {"value": 1.0 / dt, "unit": "proofs/s", "cores": host_threads, "kind": "port",
+                        "sample": "1 email of the workload (witness + full prove), %.1f s" % dt,
+                        "gpu_proof_bit_exact": proofs_gpu[:256] == proof_cpu}
+
     # ---- BASELINE configs[3] (Proof-of-Twitter circuit, 4 GPUs) and configs[4] (maxBodyLength 16384, domain 2^24, 8 GPUs):
     #      batch-parallel throughput of each rank's share, and ONE config-[4] proof sharded across all ranks (N > 1)
     other = {}
@@ -414,17 +425,6 @@ def main():
     except Exception:
         roofline["imad"] = None
     stages = {k: (v["ms"] / max(1, v["count"])) for k, v in prof.items()}
-
-    cpu_baseline = None
-    if not args.skip_cpu_baseline:
-        dt, proof_cpu, _ = cpu_reference_proof(z, circuit, zk, packed_list[0], host_threads, rs=(12345, 67890))
-        # same email, same (r, s) on the GPU: full-size bit-exact parity check on the side
-        rs = (12345).to_bytes(32, "little") + (67890).to_bytes(32, "little")
-        ctx.witness(packed_list[0], 1, want_witness=False)
-        proofs_gpu, _, _ = ctx.prove(1, rs)
-        cpu_baseline = {"value": 1.0 / dt, "unit": "proofs/s", "cores": host_threads, "kind": "port",
-                        "sample": "1 email of the workload (witness + full prove), %.1f s" % dt,
-                        "gpu_proof_bit_exact": proofs_gpu[:256] == proof_cpu}
 
     line = {"metric": "EmailVerifier proofs/sec (witness+prove)", "value": value, "unit": "proofs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_value / args.steps, "higher_is_better": True,

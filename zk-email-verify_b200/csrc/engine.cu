@@ -629,6 +629,10 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         terms.reserve(2 * c.lc_var.size() + 16);
         auto lc_len = [&](uint32_t id) { return c.lc_ptr[id + 1] - c.lc_ptr[id]; };
         const std::vector<uint32_t>& coef_word = x->coef_word;
+        // the device's big-integer hint works on at most 20 limbs (witness.cu: fpmul_hint_dev); refuse larger FpMul
+        // instances here instead of producing a witness that fails its constraints later
+        for (const WOp& o : c.ops)
+            if (o.code == OP_FPMUL && c.aux[o.a + 1] > 20) throw std::runtime_error("FpMul with k = " + std::to_string(c.aux[o.a + 1]) + " limbs exceeds the device hint's limit of 20");
         std::vector<uint32_t> order;
         std::vector<uint64_t> keys;
         for (uint32_t lvl = 0; lvl < c.n_levels(); ++lvl) {
