@@ -95,9 +95,10 @@ class _DevVec:
         self.__cuda_array_interface__ = {"shape": (n_elems, 32), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None}
 
 
-def prove_sharded(ctx, packed_input: bytes, rs: bytes | None = None, group=None):
+def prove_sharded(ctx, packed_input: bytes | None, rs: bytes | None = None, group=None):
     """One Groth16 proof computed by all ranks of `group` together (every rank passes the same input and, for a
-    reproducible proof, the same 64-byte (r, s)).  Returns (proof bytes, public signal bytes, status) on every rank."""
+    reproducible proof, the same 64-byte (r, s)).  packed_input = None: the witness already resident in the context
+    (zke_witness / zke_load_witness) is proved.  Returns (proof bytes, public signal bytes, status) on every rank."""
     import ctypes
     import torch
     import torch.distributed as dist
@@ -110,7 +111,8 @@ def prove_sharded(ctx, packed_input: bytes, rs: bytes | None = None, group=None)
         if rc != 0:
             raise L.ZkeError(err.value.decode())
 
-    ctx.witness(packed_input, 1, want_witness=False, raise_on_fail=False)       # replicated: every GPU needs the witness
+    if packed_input is not None:
+        ctx.witness(packed_input, 1, want_witness=False, raise_on_fail=False)   # replicated: every GPU needs the witness
     ok(L.zke_shard_begin(ctx.handle, rank, world, err, L.ERRCAP))
     n = L.c_size_t()
     vecs = []
