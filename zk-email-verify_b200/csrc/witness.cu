@@ -14,6 +14,7 @@
 #include "device_engine.cuh"
 #include "lc_term.cuh"
 #include "bigdiv.hpp"
+#include <cstdlib>
 
 namespace zke {
 namespace dev {
@@ -113,7 +114,11 @@ __device__ __forceinline__ void stage_terms(const DevProgram& P, uint2* buf, con
     for (uint32_t i = threadIdx.x; i < hdr.y / 2; i += WITNESS_THREADS) cp_async16(dst + i, src + i);
 }
 
-__global__ void __launch_bounds__(WITNESS_THREADS)
+// MINB = 2 caps the kernel at 64 registers per thread (half of an SM's register file per CTA instead of all of it), so
+// that the proving kernels of the previous batch can share the SM with a witness CTA when batches are pipelined
+// (zke_fullprove_submit): a witness CTA is latency-bound and leaves the multiplier pipe idle.
+template <int MINB>
+__global__ void __launch_bounds__(WITNESS_THREADS, MINB)
 witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, const uint8_t* __restrict__ inputs, uint32_t batch) {
     extern __shared__ uint4 witness_smem[];
     uint2* const term_buf = reinterpret_cast<uint2*>(witness_smem);   // 2 x WITNESS_TERM_BUF
@@ -190,11 +195,15 @@ static const size_t WITNESS_SMEM = 2 * (size_t)WITNESS_TERM_BUF * sizeof(uint2);
 // The opt-in to > 48 KB of dynamic shared memory is a per-device (per-context) function attribute: the engine calls
 // this from select_device() for every device it touches, and checks the result.
 cudaError_t configure_witness_kernel() {
-    return cudaFuncSetAttribute(witness_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WITNESS_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(witness_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WITNESS_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(witness_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WITNESS_SMEM);
 }
 
 void launch_witness(const DevProgram& P, uint8_t* w_all, size_t stride_elems, const uint8_t* inputs, uint32_t batch, cudaStream_t st) {
-    witness_kernel<<<batch, WITNESS_THREADS, WITNESS_SMEM, st>>>(P, w_all, stride_elems, inputs, batch);
+    static const bool slim = getenv("ZKE_WITNESS_SLIM") && atoi(getenv("ZKE_WITNESS_SLIM")) != 0;
+    if (slim) witness_kernel<2><<<batch, WITNESS_THREADS, WITNESS_SMEM, st>>>(P, w_all, stride_elems, inputs, batch);
+    else witness_kernel<1><<<batch, WITNESS_THREADS, WITNESS_SMEM, st>>>(P, w_all, stride_elems, inputs, batch);
     ZKE_COUNT_LAUNCH(1);
 }
 
