@@ -343,6 +343,7 @@ const void* zke_circuit_array(const zke_circuit* c, int which, size_t* n) {
         case ZKE_ARR_LC_PTR: RET(k.lc_ptr); case ZKE_ARR_LC_VAR: RET(k.lc_var); case ZKE_ARR_LC_COEF: RET(k.lc_coef);
         case ZKE_ARR_AUX: RET(k.aux);
         case ZKE_ARR_SCOPE_OF_CONSTRAINT: RET(k.scope_of_constraint);
+        case ZKE_ARR_SHA_BLOCKS: RET(k.sha_flat);
         default: *n = 0; return nullptr;
     }
 #undef RET

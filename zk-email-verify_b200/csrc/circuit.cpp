@@ -251,6 +251,14 @@ Circuit Builder::finalize() {
         if (op.code == OP_SHRAND || op.code == OP_INVZ) remap(op.a);
     }
     // (aux holds only real variables: hint_fpmul operands are witness signals)
+    for (auto& blk : c.sha_blocks) { blk.temp_begin += m; blk.temp_end += m; }   // raw temp indices -> slot numbers
+    c.sha_flat.clear();
+    c.sha_flat.push_back((uint32_t)c.sha_blocks.size());
+    for (auto& blk : c.sha_blocks) {
+        c.sha_flat.insert(c.sha_flat.end(), {blk.var_begin, blk.var_end, blk.temp_begin, blk.temp_end, (uint32_t)(blk.desc.size() / 2)});
+        c.sha_flat.insert(c.sha_flat.end(), blk.inputs.begin(), blk.inputs.end());
+        c.sha_flat.insert(c.sha_flat.end(), blk.desc.begin(), blk.desc.end());
+    }
 
     // Fuse "scratch <- LC; bits <- (scratch >> k) & mask" into OP_SHRLC when the scratch slot feeds nothing else:
     // the shift ops then sit one dependency level earlier (13.9 k -> 10.8 k levels for the default EmailVerifier).

@@ -70,6 +70,28 @@ struct WOp {
     uint32_t a, b, c;
 };
 
+// One Sha256compression instance as the front-end built it (gadgets.cpp: sha256_compression): every signal the gadget
+// creates is a bit of some 64-bit quantity of the compression (a sigma / Ch / Maj word, an AND of two rotations, one of
+// the adder sums), so a device can produce all of them from ONE native compression instead of walking the gadget's
+// ~320 dependency levels.  The witness program itself (Circuit::ops) is unchanged - the CPU oracle walks it - the
+// record only lets the engine substitute the sub-program (engine.cu: do_open).
+struct ShaBlock {
+    uint32_t var_begin = 0, var_end = 0;      // signals created by the gadget: [var_begin, var_end), one descriptor each
+    uint32_t temp_begin = 0, temp_end = 0;    // scratch slots created by the gadget (absolute slot numbers after finalize)
+    // 768 inputs: hin[256] (8 words, LSB first) then inp[512] (16 words, MSB first): a variable, or SHA_CONST0 / SHA_CONST1
+    std::vector<uint32_t> inputs;
+    std::vector<uint32_t> desc;               // 2 words per created signal: {variable, quantity << 8 | bit}
+};
+static const uint32_t SHA_CONST0 = 0xfffffffeu, SHA_CONST1 = 0xffffffffu;
+// quantities: group * 64 + index (index = round / schedule step t, or the state word for SHA_Q_FS)
+enum ShaQuantity : uint32_t {
+    SHA_Q_S1MID = 0, SHA_Q_S1 = 1, SHA_Q_S0MID = 2, SHA_Q_S0 = 3, SHA_Q_WSUM = 4,                       // message schedule, t = 16..63
+    SHA_Q_BS1MID = 5, SHA_Q_BS1 = 6, SHA_Q_CH = 7, SHA_Q_T1SUM = 8, SHA_Q_BS0MID = 9, SHA_Q_BS0 = 10,   // rounds, t = 0..63
+    SHA_Q_MAJMID = 11, SHA_Q_MAJ = 12, SHA_Q_T2SUM = 13, SHA_Q_SUME = 14, SHA_Q_SUMA = 15,
+    SHA_Q_FS = 16,                                                                                      // final sums, i = 0..7
+    SHA_Q_GROUPS = 17
+};
+
 struct SignalGroup {
     std::string name;
     uint32_t first;  // first witness index
@@ -101,6 +123,11 @@ struct Circuit {
     std::vector<uint32_t> level_ptr;
     std::vector<uint32_t> lc_ptr, lc_var, lc_coef;  // LC pool referenced by OP_LIN / OP_QUAD
     std::vector<uint32_t> aux;
+
+    std::vector<ShaBlock> sha_blocks;   // Sha256compression instances eligible for native evaluation (may be empty)
+    // flat image of sha_blocks: {n_blocks, then per block: var_begin, var_end, temp_begin, temp_end, n_desc, inputs[768],
+    // desc[2 n_desc]} (built by finalize; ZKE_ARR_SHA_BLOCKS)
+    std::vector<uint32_t> sha_flat;
 
     uint32_t n_levels() const { return level_ptr.empty() ? 0 : (uint32_t)level_ptr.size() - 1; }
     const SignalGroup* find_group(const std::string& n) const;
@@ -144,6 +171,8 @@ class Builder {
     Circuit finalize();
 
     uint32_t num_vars() const { return next_var_; }
+    uint32_t num_temps() const { return next_temp_; }
+    void add_sha_block(ShaBlock&& blk) { c_.sha_blocks.push_back(std::move(blk)); }   // temp range as raw temp indices
     uint32_t num_constraints() const { return (uint32_t)c_.scope_of_constraint.size(); }
 
    private:

@@ -27,7 +27,9 @@ extern unsigned long long g_kernel_launches;
 static const uint32_t WOP_NOP = 15;
 struct DevProgram {
     const uint4* ops;            // [n_iters][WITNESS_THREADS]
-    const uint2* iter_hdr;       // [n_iters + 2]: {first term (even), term count (even)}
+    const uint4* iter_hdr;       // [n_iters + 2]: {first term (even), term count (even), first cooperative op, their count}
+    const uint32_t* coop;        // cooperative ops of the iterations: offsets into `aux` of native Sha256compression tables
+                                 // ({n_desc, inputs[768], desc[n_desc][2]}, circuit.hpp: ShaBlock) - executed by the whole CTA
     const uint2* terms;
     const uint32_t* aux;
     const uint8_t* coef_r;       // [n_coefs][32]: coefficient * R mod r  (Montgomery-scaled: (cR) (x) w = c*w)

@@ -161,7 +161,7 @@ struct zke_ctx {
     uint32_t n_vars = 0, n_public = 0, n_inputs = 0;
     cudaStream_t stream = nullptr;          // witness stream (highest priority)
     // circuit on device
-    DevBuf ops, iter_hdr, lc_terms, aux, coef_r, small_inv;
+    DevBuf ops, iter_hdr, lc_terms, aux, coop, coef_r, small_inv;
     std::vector<uint32_t> coef_word;   // per interned coefficient: index | k << 16 | kind << 24 (lc_term.cuh)
     std::vector<uint32_t> iter_info;   // per iteration {first op's record word 1, live ops, terms} (diagnostics)
     DevBuf a_ptr, a_terms, b_ptr, b_terms, c_ptr, c_terms;
@@ -633,18 +633,116 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         // instances here instead of producing a witness that fails its constraints later
         for (const WOp& o : c.ops)
             if (o.code == OP_FPMUL && c.aux[o.a + 1] > 20) throw std::runtime_error("FpMul with k = " + std::to_string(c.aux[o.a + 1]) + " limbs exceeds the device hint's limit of 20");
+        // ---- native Sha256compression (circuit.hpp: ShaBlock; ZKE_NATIVE_SHA=0 keeps the gadget's own ops): the ops that
+        // define the signals / scratch slots of a recorded instance are replaced by ONE cooperative op per instance and
+        // the program is levelised again - the chained compressions then cost one level each instead of ~320.
+        bool native_sha = !c.sha_blocks.empty();
+        if (const char* e = getenv("ZKE_NATIVE_SHA")) native_sha = native_sha && atoi(e) != 0;
+        static const uint32_t XOP_SHA = 6;
+        std::vector<WOp> xops;                         // code XOP_SHA: a = index of the block
+        std::vector<uint32_t> xlevel_ptr;              // ops of level l: [xlevel_ptr[l], xlevel_ptr[l + 1])
+        std::vector<uint32_t> aux = c.aux;
+        std::vector<uint32_t> sha_aux_off(c.sha_blocks.size(), 0);
+        if (!native_sha) {
+            xops = c.ops;
+            xlevel_ptr = c.level_ptr;
+        } else {
+            const uint32_t total = c.n_vars + c.n_temps;
+            std::vector<int32_t> owner(total, -1);     // slot -> block that defines it
+            for (size_t bi = 0; bi < c.sha_blocks.size(); ++bi) {
+                const ShaBlock& B = c.sha_blocks[bi];
+                for (uint32_t v = B.var_begin; v < B.var_end; ++v) owner[v] = (int32_t)bi;
+                for (uint32_t v = B.temp_begin; v < B.temp_end; ++v) owner[v] = (int32_t)bi;
+                sha_aux_off[bi] = (uint32_t)aux.size();
+                aux.push_back((uint32_t)(B.desc.size() / 2));
+                aux.insert(aux.end(), B.inputs.begin(), B.inputs.end());
+                aux.insert(aux.end(), B.desc.begin(), B.desc.end());
+            }
+            // Order: c.ops is in level order (producers before consumers).  A block's op is inserted right after the
+            // producer of its LAST-defined input: everything it reads precedes it, and everything that reads its outputs
+            // (the final-sum bits, originally defined after all of the block's inputs) follows it.
+            std::vector<int64_t> def_pos(total, -1);
+            for (size_t i = 0; i < c.ops.size(); ++i) {
+                const WOp& o = c.ops[i];
+                const uint32_t nd = o.code == OP_FPMUL ? 2 * c.aux[o.a + 1] : 1;
+                for (uint32_t j = 0; j < nd; ++j) def_pos[o.dst + j] = (int64_t)i;
+            }
+            std::vector<std::vector<uint32_t>> blocks_at(c.ops.size() + 1);
+            for (size_t bi = 0; bi < c.sha_blocks.size(); ++bi) {
+                int64_t pos = 0;
+                for (uint32_t v : c.sha_blocks[bi].inputs) if (v < SHA_CONST0) pos = std::max(pos, def_pos[v] + 1);
+                blocks_at[(size_t)pos].push_back((uint32_t)bi);
+            }
+            std::vector<WOp> kept;
+            kept.reserve(c.ops.size());
+            for (size_t i = 0; i <= c.ops.size(); ++i) {
+                for (uint32_t bi : blocks_at[i]) kept.push_back(WOp{XOP_SHA, c.sha_blocks[bi].var_begin, bi, 0, 0});
+                if (i < c.ops.size() && owner[c.ops[i].dst] < 0) kept.push_back(c.ops[i]);
+            }
+            // levelise (the same rules as Builder::finalize, plus the multi-output block op)
+            std::vector<uint32_t> level(total, 0), op_level(kept.size(), 0);
+            std::vector<uint8_t> defined(total, 0);
+            defined[0] = 1;
+            for (auto& g : c.groups) if (g.kind != 0) for (uint32_t i = 0; i < g.count; ++i) defined[g.first + i] = 1;
+            auto need = [&](uint32_t v) -> uint32_t {
+                if (!defined[v]) throw std::runtime_error("native SHA substitution: an op reads an unassigned signal");
+                return level[v];
+            };
+            auto lc_level = [&](uint32_t id) { uint32_t l = 0; for (uint32_t k = c.lc_ptr[id]; k < c.lc_ptr[id + 1]; ++k) l = std::max(l, need(c.lc_var[k])); return l; };
+            uint32_t max_level = 0;
+            for (size_t i = 0; i < kept.size(); ++i) {
+                const WOp& o = kept[i];
+                uint32_t l = 0;
+                switch (o.code) {
+                    case OP_LIN: case OP_SHRLC: l = lc_level(o.a); break;
+                    case OP_QUAD: l = std::max(lc_level(o.a), std::max(lc_level(o.b), lc_level(o.c))); break;
+                    case OP_SHRAND: case OP_INVZ: l = need(o.a); break;
+                    case OP_FPMUL: { const uint32_t kk = c.aux[o.a + 1]; for (uint32_t j = 0; j < 3 * kk; ++j) l = std::max(l, need(c.aux[o.a + 2 + j])); break; }
+                    case XOP_SHA: for (uint32_t v : c.sha_blocks[o.a].inputs) if (v < SHA_CONST0) l = std::max(l, need(v)); break;
+                    default: throw std::runtime_error("bad opcode");
+                }
+                l += 1;
+                if (o.code == XOP_SHA) {
+                    const ShaBlock& B = c.sha_blocks[o.a];
+                    for (uint32_t v = B.var_begin; v < B.var_end; ++v) { defined[v] = 1; level[v] = l; }
+                } else if (o.code == OP_FPMUL) {
+                    const uint32_t kk = c.aux[o.a + 1];
+                    for (uint32_t j = 0; j < 2 * kk; ++j) { defined[o.dst + j] = 1; level[o.dst + j] = l; }
+                } else {
+                    defined[o.dst] = 1; level[o.dst] = l;
+                }
+                op_level[i] = l;
+                max_level = std::max(max_level, l);
+            }
+            xlevel_ptr.assign(max_level + 1, 0);
+            for (uint32_t l : op_level) xlevel_ptr[l]++;                 // levels are 1-based here
+            { uint32_t run = 0; for (uint32_t l = 1; l <= max_level; ++l) { const uint32_t n = xlevel_ptr[l]; xlevel_ptr[l] = run; run += n; } xlevel_ptr[0] = 0; }
+            xops.resize(kept.size());
+            { std::vector<uint32_t> cursor(xlevel_ptr.begin(), xlevel_ptr.end()); for (size_t i = 0; i < kept.size(); ++i) xops[cursor[op_level[i]]++] = kept[i]; }
+            std::vector<uint32_t> lp(max_level + 1);
+            for (uint32_t l = 1; l <= max_level; ++l) lp[l - 1] = xlevel_ptr[l];
+            lp[max_level] = (uint32_t)kept.size();
+            xlevel_ptr.swap(lp);
+        }
+        const uint32_t n_xlevels = xlevel_ptr.empty() ? 0 : (uint32_t)xlevel_ptr.size() - 1;
+        std::vector<uint32_t> coop;                     // cooperative ops, grouped by iteration
         std::vector<uint32_t> order;
         std::vector<uint64_t> keys;
-        for (uint32_t lvl = 0; lvl < c.n_levels(); ++lvl) {
-            const uint32_t beg = c.level_ptr[lvl], end = c.level_ptr[lvl + 1];
-            order.resize(end - beg);
-            for (uint32_t i = beg; i < end; ++i) order[i - beg] = i;
+        for (uint32_t lvl = 0; lvl < n_xlevels; ++lvl) {
+            const uint32_t beg = xlevel_ptr[lvl], end = xlevel_ptr[lvl + 1];
+            order.clear();
+            const uint32_t coop_first = (uint32_t)coop.size();
+            for (uint32_t i = beg; i < end; ++i) {
+                if (xops[i].code == XOP_SHA) coop.push_back(sha_aux_off[xops[i].a]);
+                else order.push_back(i);
+            }
+            uint32_t coop_left = (uint32_t)coop.size() - coop_first;   // attached to the level's first iteration
             // Sort key: kind, then the positions of the terms that need a product (coefficient other than +-1) in the
             // flattened [A | B | C] term list, then the term count.  Within an LC the product terms are emitted first
             // (addition commutes), so the ops of a warp take the product branch of eval_lcs in the same term slots -
             // or not at all: a warp only pays for a Montgomery product where some lane needs one.
             auto key = [&](uint32_t i) -> uint64_t {
-                const WOp& o = c.ops[i];
+                const WOp& o = xops[i];
                 if (o.code == OP_FPMUL) return ~0ull;
                 if (o.code == OP_INVZ) return 1ull << 62;
                 if (o.code == OP_SHRAND) return 0;
@@ -660,15 +758,17 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                 }
                 return ((uint64_t)(o.code == OP_QUAD ? 2 : 1) << 60) | (mask << 8) | std::min<uint32_t>(pos, 255);
             };
-            keys.resize(end - beg);
-            for (uint32_t i = beg; i < end; ++i) keys[i - beg] = key(i);
-            std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return keys[x - beg] > keys[y - beg]; });
-            for (size_t base = 0; base < order.size(); base += T) {
+            std::vector<std::pair<uint64_t, uint32_t>> keyed(order.size());
+            for (size_t i = 0; i < order.size(); ++i) keyed[i] = {key(order[i]), order[i]};
+            std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<uint64_t, uint32_t>& x, const std::pair<uint64_t, uint32_t>& y) { return x.first > y.first; });
+            for (size_t i = 0; i < order.size(); ++i) order[i] = keyed[i].second;
+            const size_t n_regular = order.size();
+            for (size_t base = 0; base < std::max<size_t>(n_regular, coop_left ? 1 : 0); base += T) {
                 const uint32_t first_term = (uint32_t)(terms.size() / 2);
                 for (uint32_t t = 0; t < T; ++t) {
                     uint32_t rec[4] = {0, dev::WOP_NOP, 0, 0};
-                    if (base + t < order.size()) {
-                        const WOp& o = c.ops[order[base + t]];
+                    if (base + t < n_regular) {
+                        const WOp& o = xops[order[base + t]];
                         rec[0] = o.dst;
                         if (o.code == OP_LIN || o.code == OP_QUAD || o.code == OP_SHRLC) {
                             const uint32_t ids[3] = {o.a, o.b, o.c};
@@ -699,21 +799,25 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                 if ((terms.size() / 2) & 1) { terms.push_back(0); terms.push_back(0); }   // keep blocks 16-byte aligned
                 hdr.push_back(first_term);
                 hdr.push_back((uint32_t)(terms.size() / 2) - first_term);
+                hdr.push_back(coop_first);
+                hdr.push_back(coop_left);
+                coop_left = 0;
                 x->iter_info.push_back(packed[packed.size() - 4 * T + 1]);
-                x->iter_info.push_back((uint32_t)std::min<size_t>(T, order.size() - base));
+                x->iter_info.push_back((uint32_t)std::min<size_t>(T, n_regular > base ? n_regular - base : 0));
                 x->iter_info.push_back((uint32_t)(terms.size() / 2) - first_term);
             }
         }
-        const uint32_t n_iters = (uint32_t)(hdr.size() / 2);
-        for (int q = 0; q < 4; ++q) hdr.push_back(q & 1 ? 0 : (uint32_t)(terms.size() / 2));   // two sentinel headers
+        const uint32_t n_iters = (uint32_t)(hdr.size() / 4);
+        for (int q = 0; q < 2; ++q) { hdr.push_back((uint32_t)(terms.size() / 2)); hdr.push_back(0); hdr.push_back(0); hdr.push_back(0); }   // two sentinel headers
         if (packed.empty()) packed.resize(4 * T, 0);
         for (int q = 0; q < 8; ++q) terms.push_back(0);
         x->ops.upload(packed);
         x->iter_hdr.upload(hdr);
         x->lc_terms.upload(terms);
-        std::vector<uint32_t> aux = c.aux;
         if (aux.empty()) aux.push_back(0);
         x->aux.upload(aux);
+        if (coop.empty()) coop.push_back(0);
+        x->coop.upload(coop);
         const uint32_t NSMALL = 4096;
         std::vector<Fr> inv(NSMALL);
         for (uint32_t i = 0; i < NSMALL; ++i) inv[i] = Fr::from_u64(i);
@@ -722,7 +826,7 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         for (uint32_t i = 0; i < NSMALL; ++i) inv_std[i] = inv[i].to_u256();
         x->small_inv.upload(inv_std);
         dev::DevProgram& P = x->prog;
-        P.ops = (const uint4*)x->ops.p; P.iter_hdr = (const uint2*)x->iter_hdr.p;
+        P.ops = (const uint4*)x->ops.p; P.iter_hdr = (const uint4*)x->iter_hdr.p; P.coop = (const uint32_t*)x->coop.p;
         P.terms = (const uint2*)x->lc_terms.p; P.aux = (const uint32_t*)x->aux.p; P.coef_r = x->coef_r.p;
         P.small_inv = x->small_inv.p; P.n_small_inv = NSMALL;
         P.trace = nullptr;

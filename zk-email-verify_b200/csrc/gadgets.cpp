@@ -120,39 +120,67 @@ LCVec sha256_iv_bits() {
 static LCVec rotr(const LCVec& in, uint32_t r) { LCVec o(32); for (uint32_t i = 0; i < 32; ++i) o[i] = in[(i + r) % 32]; return o; }
 static LCVec shr(const LCVec& in, uint32_t r) { LCVec o(32); for (uint32_t i = 0; i < 32; ++i) o[i] = (i + r >= 32) ? LC() : in[i + r]; return o; }
 
-static LCVec xor3(Builder& b, const LCVec& x, const LCVec& y, const LCVec& z) {
+// Recorder of one Sha256compression instance (circuit.hpp: ShaBlock): whenever a gadget call returns a signal it has just
+// created, the signal is noted together with the native quantity and bit whose value it carries.
+struct ShaRecorder {
+    ShaBlock blk;
+    bool ok = true;
+    void note(const Builder& b, uint32_t var_mark, const LC& e, uint32_t group, uint32_t index, uint32_t bit) {
+        Var v;
+        if (b.num_vars() == var_mark) return;                       // the call folded into existing signals / constants
+        if (b.num_vars() != var_mark + 1 || !e.is_single_var(&v) || v != var_mark) { ok = false; return; }
+        blk.desc.push_back(v);
+        blk.desc.push_back(((group * 64 + index) << 8) | bit);
+    }
+};
+static thread_local ShaRecorder* g_sha_rec = nullptr;
+#define SHA_NOTE(expr_lc, group, index, bit) do { if (g_sha_rec) g_sha_rec->note(b, mark_, (expr_lc), (group), (index), (bit)); } while (0)
+
+static LCVec xor3(Builder& b, const LCVec& x, const LCVec& y, const LCVec& z, uint32_t q_mid, uint32_t q_out, uint32_t t) {
     // mid[k] <== b[k]*c[k]; out[k] <== a[k] * (1 -2*b[k] -2*c[k] +4*mid[k]) + b[k] + c[k] -2*mid[k];
     const Fr two = Fr::from_u64(2), four = Fr::from_u64(4);
     LCVec o(32);
     for (int k = 0; k < 32; ++k) {
+        uint32_t mark_ = b.num_vars();
         LC mid = b.mul(y[k], z[k]);
+        SHA_NOTE(mid, q_mid, t, (uint32_t)k);
+        mark_ = b.num_vars();
         o[k] = b.mul_add(x[k], one_lc() - y[k] * two - z[k] * two + mid * four, y[k] + z[k] - mid * two);
+        SHA_NOTE(o[k], q_out, t, (uint32_t)k);
     }
     return o;
 }
-static LCVec small_sigma(Builder& b, const LCVec& in, uint32_t ra, uint32_t rb, uint32_t rc) {
-    return xor3(b, rotr(in, ra), rotr(in, rb), shr(in, rc));
+static LCVec small_sigma(Builder& b, const LCVec& in, uint32_t ra, uint32_t rb, uint32_t rc, uint32_t q_mid, uint32_t q_out, uint32_t t) {
+    return xor3(b, rotr(in, ra), rotr(in, rb), shr(in, rc), q_mid, q_out, t);
 }
-static LCVec big_sigma(Builder& b, const LCVec& in, uint32_t ra, uint32_t rb, uint32_t rc) {
-    return xor3(b, rotr(in, ra), rotr(in, rb), rotr(in, rc));
+static LCVec big_sigma(Builder& b, const LCVec& in, uint32_t ra, uint32_t rb, uint32_t rc, uint32_t q_mid, uint32_t q_out, uint32_t t) {
+    return xor3(b, rotr(in, ra), rotr(in, rb), rotr(in, rc), q_mid, q_out, t);
 }
-static LCVec ch_t(Builder& b, const LCVec& x, const LCVec& y, const LCVec& z) {
+static LCVec ch_t(Builder& b, const LCVec& x, const LCVec& y, const LCVec& z, uint32_t t) {
     LCVec o(32);
-    for (int k = 0; k < 32; ++k) o[k] = b.mul_add(x[k], y[k] - z[k], z[k]);   // out <== a*(b-c) + c
+    for (int k = 0; k < 32; ++k) {
+        const uint32_t mark_ = b.num_vars();
+        o[k] = b.mul_add(x[k], y[k] - z[k], z[k]);   // out <== a*(b-c) + c
+        SHA_NOTE(o[k], SHA_Q_CH, t, (uint32_t)k);
+    }
     return o;
 }
-static LCVec maj_t(Builder& b, const LCVec& x, const LCVec& y, const LCVec& z) {
+static LCVec maj_t(Builder& b, const LCVec& x, const LCVec& y, const LCVec& z, uint32_t t) {
     const Fr two = Fr::from_u64(2);
     LCVec o(32);
     for (int k = 0; k < 32; ++k) {
+        uint32_t mark_ = b.num_vars();
         LC mid = b.mul(y[k], z[k]);
+        SHA_NOTE(mid, SHA_Q_MAJMID, t, (uint32_t)k);
+        mark_ = b.num_vars();
         o[k] = b.mul_add(x[k], y[k] + z[k] - mid * two, mid);                 // out <== a*(b+c-2*mid) + mid
+        SHA_NOTE(o[k], SHA_Q_MAJ, t, (uint32_t)k);
     }
     return o;
 }
 static uint32_t nbits_of(uint64_t a) { uint64_t n = 1; uint32_t r = 0; while (n - 1 < a) { r++; n *= 2; } return r; }
 
-static LCVec binsum(Builder& b, const std::vector<LCVec>& ins) {
+static LCVec binsum(Builder& b, const std::vector<LCVec>& ins, uint32_t q_sum, uint32_t t) {
     ScopeGuard g(b, "BinSum");
     const uint32_t n = 32, ops = (uint32_t)ins.size();
     const uint32_t nout = nbits_of(((1ull << n) - 1) * ops);
@@ -163,8 +191,10 @@ static LCVec binsum(Builder& b, const std::vector<LCVec>& ins) {
     LCVec out(nout);
     LC lout;
     for (uint32_t k = 0; k < nout; ++k) {
+        const uint32_t mark_ = b.num_vars();
         Var bit = b.hint_shrand(src, k, 1);            // out[k] <-- (lin >> k) & 1
         out[k] = LC(bit);
+        SHA_NOTE(out[k], q_sum, t, k);
         b.enforce_mul(out[k], out[k] - one_lc(), LC());
         lout.add_term(bit, fr_pow2(k));
     }
@@ -176,6 +206,22 @@ static LCVec low32(const LCVec& v) { return LCVec(v.begin(), v.begin() + 32); }
 LCVec sha256_compression(Builder& b, const LCVec& hin, const LCVec& inp) {
     ScopeGuard g(b, "Sha256compression");
     if (hin.size() != 256 || inp.size() != 512) throw std::runtime_error("Sha256compression: bad sizes");
+    // record the instance for native evaluation (circuit.hpp: ShaBlock) when every input is a signal or a constant bit
+    ShaRecorder rec;
+    rec.blk.var_begin = b.num_vars();
+    rec.blk.temp_begin = b.num_temps();
+    rec.blk.inputs.resize(768);
+    for (int i = 0; i < 768 && rec.ok; ++i) {
+        const LC& e = i < 256 ? hin[i] : inp[i - 256];
+        Var v;
+        if (e.is_zero()) rec.blk.inputs[i] = SHA_CONST0;
+        else if (e.is_const() && e.const_value() == Fr::one()) rec.blk.inputs[i] = SHA_CONST1;
+        else if (e.is_single_var(&v)) rec.blk.inputs[i] = v;
+        else rec.ok = false;
+    }
+    ShaRecorder* const outer = g_sha_rec;
+    g_sha_rec = rec.ok ? &rec : nullptr;
+    struct Restore { ShaRecorder* p; ~Restore() { g_sha_rec = p; } } restore{outer};
     std::vector<LCVec> w(64);
     for (int t = 0; t < 64; ++t) {
         if (t < 16) {
@@ -183,9 +229,9 @@ LCVec sha256_compression(Builder& b, const LCVec& hin, const LCVec& inp) {
             for (int k = 0; k < 32; ++k) w[t][k] = inp[t * 32 + 31 - k];
         } else {
             // SigmaPlus: BinSum(32,4) of sigma1(in2), in7, sigma0(in15), in16
-            LCVec s1 = small_sigma(b, w[t - 2], 17, 19, 10);
-            LCVec s0 = small_sigma(b, w[t - 15], 7, 18, 3);
-            w[t] = low32(binsum(b, {s1, w[t - 7], s0, w[t - 16]}));
+            LCVec s1 = small_sigma(b, w[t - 2], 17, 19, 10, SHA_Q_S1MID, SHA_Q_S1, (uint32_t)t);
+            LCVec s0 = small_sigma(b, w[t - 15], 7, 18, 3, SHA_Q_S0MID, SHA_Q_S0, (uint32_t)t);
+            w[t] = low32(binsum(b, {s1, w[t - 7], s0, w[t - 16]}, SHA_Q_WSUM, (uint32_t)t));
         }
     }
     LCVec st[8];
@@ -193,23 +239,29 @@ LCVec sha256_compression(Builder& b, const LCVec& hin, const LCVec& inp) {
     LCVec &a = st[0], &bb = st[1], &c = st[2], &d = st[3], &e = st[4], &f = st[5], &gg = st[6], &h = st[7];
     for (int t = 0; t < 64; ++t) {
         // T1 = BinSum(32,5)(h, BigSigma(6,11,25)(e), Ch(e,f,g), k, w)
-        LCVec bs1 = big_sigma(b, e, 6, 11, 25);
-        LCVec chv = ch_t(b, e, f, gg);
-        LCVec t1 = low32(binsum(b, {h, bs1, chv, const_word(SHA_K[t]), w[t]}));
+        LCVec bs1 = big_sigma(b, e, 6, 11, 25, SHA_Q_BS1MID, SHA_Q_BS1, (uint32_t)t);
+        LCVec chv = ch_t(b, e, f, gg, (uint32_t)t);
+        LCVec t1 = low32(binsum(b, {h, bs1, chv, const_word(SHA_K[t]), w[t]}, SHA_Q_T1SUM, (uint32_t)t));
         // T2 = BinSum(32,2)(BigSigma(2,13,22)(a), Maj(a,b,c))
-        LCVec bs0 = big_sigma(b, a, 2, 13, 22);
-        LCVec mj = maj_t(b, a, bb, c);
-        LCVec t2 = low32(binsum(b, {bs0, mj}));
-        LCVec sume = low32(binsum(b, {d, t1}));
-        LCVec suma = low32(binsum(b, {t1, t2}));
+        LCVec bs0 = big_sigma(b, a, 2, 13, 22, SHA_Q_BS0MID, SHA_Q_BS0, (uint32_t)t);
+        LCVec mj = maj_t(b, a, bb, c, (uint32_t)t);
+        LCVec t2 = low32(binsum(b, {bs0, mj}, SHA_Q_T2SUM, (uint32_t)t));
+        LCVec sume = low32(binsum(b, {d, t1}, SHA_Q_SUME, (uint32_t)t));
+        LCVec suma = low32(binsum(b, {t1, t2}, SHA_Q_SUMA, (uint32_t)t));
         h = gg; gg = f; f = e; e = sume; d = c; c = bb; bb = a; a = suma;
     }
     LCVec out(256);
     for (int i = 0; i < 8; ++i) {
         LCVec hi(hin.begin() + 32 * i, hin.begin() + 32 * (i + 1));
-        LCVec fs = binsum(b, {hi, st[i]});
+        LCVec fs = binsum(b, {hi, st[i]}, SHA_Q_FS, (uint32_t)i);
         for (int k = 0; k < 32; ++k) out[32 * i + 31 - k] = fs[k];
     }
+    g_sha_rec = outer;
+    rec.blk.var_end = b.num_vars();
+    rec.blk.temp_end = b.num_temps();
+    // every signal of the instance must have exactly one descriptor - otherwise the instance stays on the generic path
+    if (rec.ok && rec.blk.desc.size() == 2 * (size_t)(rec.blk.var_end - rec.blk.var_begin) && rec.blk.var_end > rec.blk.var_begin)
+        b.add_sha_block(std::move(rec.blk));
     return out;
 }
 

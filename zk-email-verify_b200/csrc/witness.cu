@@ -99,6 +99,92 @@ __device__ void fpmul_hint_dev(const DevProgram& P, uint8_t* w, uint32_t aux_off
     }
 }
 
+// ---- native Sha256compression (circuit.hpp: ShaBlock) ----------------------------------------------------------------
+// The gadget's ~30 k signals are all bits of 64-bit quantities of one plain compression: the CTA gathers the 768 input
+// bits, one thread runs the compression and leaves the quantities in shared memory, and all threads write the signals -
+// one dependency level instead of the gadget's ~320 (the 40 chained compressions of the default EmailVerifier were 60 %
+// of the witness kernel's level count).  The CPU oracle still walks the gadget's own ops, so "GPU witness == oracle
+// witness" checks this path end to end; tests/test_sha_native_table.py pins the quantity table on the CPU.
+__constant__ uint32_t SHA_K_DEV[64] = {
+    0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+    0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+    0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+    0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+    0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+    0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+static const uint32_t SHA_Q_WORDS = 17 * 64;      // quantity groups x 64 (circuit.hpp: ShaQuantity)
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, int r) { return __funnelshift_r(x, x, r); }
+
+__device__ void sha_coop(const DevProgram& P, uint8_t* w, uint32_t aux_off, unsigned long long* Q, uint32_t* inw) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t* ax = P.aux + aux_off;
+    const uint32_t n_desc = ax[0];
+    const uint32_t* src = ax + 1;
+    const uint32_t* desc = ax + 1 + 768;
+    if (tid < 24) inw[tid] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < 768; i += WITNESS_THREADS) {
+        const uint32_t s = src[i];
+        uint32_t bit;
+        if (s >= 0xfffffffeu) bit = s & 1u;                                   // SHA_CONST0 / SHA_CONST1
+        else bit = *reinterpret_cast<const uint32_t*>(w + 32ull * s) & 1u;
+        if (bit) {
+            if (i < 256) atomicOr(&inw[i >> 5], 1u << (i & 31));              // chaining words, LSB first
+            else { const uint32_t j = i - 256; atomicOr(&inw[8 + (j >> 5)], 1u << (31 - (j & 31))); }   // message words, MSB first
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t W[64];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) W[t] = inw[8 + t];
+#pragma unroll 1
+        for (int t = 16; t < 64; ++t) {
+            const uint32_t x = W[t - 2], y = W[t - 15];
+            const uint32_t s1 = rotr32(x, 17) ^ rotr32(x, 19) ^ (x >> 10), s0 = rotr32(y, 7) ^ rotr32(y, 18) ^ (y >> 3);
+            Q[0 * 64 + t] = rotr32(x, 19) & (x >> 10);
+            Q[1 * 64 + t] = s1;
+            Q[2 * 64 + t] = rotr32(y, 18) & (y >> 3);
+            Q[3 * 64 + t] = s0;
+            const unsigned long long sum = (unsigned long long)s1 + W[t - 7] + s0 + W[t - 16];
+            Q[4 * 64 + t] = sum;
+            W[t] = (uint32_t)sum;
+        }
+        uint32_t a = inw[0], b = inw[1], c = inw[2], d = inw[3], e = inw[4], f = inw[5], g = inw[6], h = inw[7];
+#pragma unroll 1
+        for (int t = 0; t < 64; ++t) {
+            const uint32_t bs1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25), ch = (e & f) ^ (~e & g);
+            Q[5 * 64 + t] = rotr32(e, 11) & rotr32(e, 25);
+            Q[6 * 64 + t] = bs1;
+            Q[7 * 64 + t] = ch;
+            const unsigned long long t1 = (unsigned long long)h + bs1 + ch + SHA_K_DEV[t] + W[t];
+            Q[8 * 64 + t] = t1;
+            const uint32_t bs0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22), mj = (a & b) ^ (a & c) ^ (b & c);
+            Q[9 * 64 + t] = rotr32(a, 13) & rotr32(a, 22);
+            Q[10 * 64 + t] = bs0;
+            Q[11 * 64 + t] = b & c;
+            Q[12 * 64 + t] = mj;
+            const unsigned long long t2 = (unsigned long long)bs0 + mj;
+            Q[13 * 64 + t] = t2;
+            const unsigned long long sume = (unsigned long long)d + (uint32_t)t1, suma = (unsigned long long)(uint32_t)t1 + (uint32_t)t2;
+            Q[14 * 64 + t] = sume;
+            Q[15 * 64 + t] = suma;
+            h = g; g = f; f = e; e = (uint32_t)sume; d = c; c = b; b = a; a = (uint32_t)suma;
+        }
+        const uint32_t st[8] = {a, b, c, d, e, f, g, h};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Q[16 * 64 + i] = (unsigned long long)inw[i] + st[i];
+    }
+    __syncthreads();
+    for (uint32_t dd = tid; dd < n_desc; dd += WITNESS_THREADS) {
+        const uint32_t var = desc[2 * dd], qk = desc[2 * dd + 1];
+        Fr o = Fr::zero();
+        o.v[0] = (uint32_t)((Q[qk >> 8] >> (qk & 255u)) & 1ull);
+        o.store(w + 32ull * var);
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -107,7 +193,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // stages the term block of one iteration into shared memory (16-byte chunks, coalesced); blocks larger than the
 // buffer are not staged - the ops of such an iteration read their terms from global memory instead
-__device__ __forceinline__ void stage_terms(const DevProgram& P, uint2* buf, const uint2& hdr) {
+__device__ __forceinline__ void stage_terms(const DevProgram& P, uint2* buf, const uint4& hdr) {
     if (hdr.y > WITNESS_TERM_BUF) return;
     const uint4* src = reinterpret_cast<const uint4*>(P.terms + hdr.x);
     uint4* dst = reinterpret_cast<uint4*>(buf);
@@ -122,6 +208,8 @@ __global__ void __launch_bounds__(WITNESS_THREADS, MINB)
 witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, const uint8_t* __restrict__ inputs, uint32_t batch) {
     extern __shared__ uint4 witness_smem[];
     uint2* const term_buf = reinterpret_cast<uint2*>(witness_smem);   // 2 x WITNESS_TERM_BUF
+    __shared__ unsigned long long sha_q[SHA_Q_WORDS];
+    __shared__ uint32_t sha_in[24];
     const uint32_t email = blockIdx.x;
     if (email >= batch) return;
     uint8_t* w = w_all + 32ull * stride_elems * email;
@@ -142,14 +230,14 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
 
     // software pipeline: op records one iteration ahead (registers), term blocks one iteration ahead (cp.async into
     // the other shared-memory buffer), iteration headers two ahead
-    uint2 hdr = P.iter_hdr[0], hdr_next = P.iter_hdr[1];
+    uint4 hdr = P.iter_hdr[0], hdr_next = P.iter_hdr[1];
     uint4 op = P.ops[tid];
     stage_terms(P, term_buf, hdr);
     cp_async_wait_all();
     __syncthreads();
 
     for (uint32_t k = 0; k < P.n_iters; ++k) {
-        const uint2 hdr_next2 = P.iter_hdr[k + 2];      // the table has two sentinel entries
+        const uint4 hdr_next2 = P.iter_hdr[k + 2];      // the table has two sentinel entries
         uint4 op_next = make_uint4(0, WOP_NOP, 0, 0);
         if (k + 1 < P.n_iters) {
             op_next = P.ops[(size_t)(k + 1) * WITNESS_THREADS + tid];
@@ -183,6 +271,9 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
         } else if (code == 4) {   // OP_FPMUL
             fpmul_hint_dev(P, w, op.z, op.x);
         }
+        // cooperative ops of this iteration (native Sha256compression): the whole CTA works on each in turn; they only
+        // read signals of earlier levels and define signals nothing else in this iteration touches
+        for (uint32_t q = 0; q < hdr.w; ++q) sha_coop(P, w, P.coop[hdr.z + q], sha_q, sha_in);
         cp_async_wait_all();
         __syncthreads();     // level barrier and hand-over of the staged term block
         if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[k] = clock64();
