@@ -56,41 +56,9 @@ ZKE_HD inline void bd_extract(const uint32_t* x, int W, uint32_t bit, uint32_t n
     }
 }
 
-// a_limbs / b_limbs / p_limbs: k values of 8 words each (witness values).  q_out / r_out: k values of 8 words each.
-// Returns 0 on success, non-zero if the parameters exceed the supported size.
-ZKE_HD inline int fpmul_hint_words(uint32_t n, uint32_t k, const uint32_t* a_limbs, const uint32_t* b_limbs,
-                                   const uint32_t* p_limbs, uint32_t* q_out, uint32_t* r_out) {
-    const int W = (int)((n * k + 256 + 31) / 32);
-    if (W > BIGDIV_MAXW || n > 128 || n == 0) return 1;
-    uint32_t A[BIGDIV_MAXW], B[BIGDIV_MAXW], P[BIGDIV_MAXW + 1];
-    uint32_t U[2 * BIGDIV_MAXW + 2];   // dividend (normalised in place), ends up holding the remainder
-    uint32_t Q[2 * BIGDIV_MAXW + 1];
-    for (int i = 0; i < W; ++i) { A[i] = 0; B[i] = 0; P[i] = 0; }
-    for (uint32_t i = 0; i < k; ++i) {
-        bd_add_shifted(A, W, a_limbs + 8 * i, n * i);
-        bd_add_shifted(B, W, b_limbs + 8 * i, n * i);
-        bd_add_shifted(P, W, p_limbs + 8 * i, n * i);
-    }
-    const int UL = 2 * W;
-    for (int i = 0; i < UL + 2; ++i) U[i] = 0;
-    for (int i = 0; i < UL + 1; ++i) Q[i] = 0;
-    for (int i = 0; i < W; ++i) {
-        uint64_t carry = 0;
-        const uint64_t ai = A[i];
-        if (ai == 0) continue;
-        for (int j = 0; j < W; ++j) {
-            uint64_t s = ai * B[j] + U[i + j] + carry;
-            U[i + j] = (uint32_t)s;
-            carry = s >> 32;
-        }
-        U[i + W] = (uint32_t)carry;
-    }
-    int t = W;
-    while (t > 0 && P[t - 1] == 0) --t;
-    if (t == 0) {  // division by zero: circom's long_div would fail its own asserts; emit zeros, constraints reject
-        for (uint32_t i = 0; i < 8 * k; ++i) { q_out[i] = 0; r_out[i] = 0; }
-        return 0;
-    }
+// Knuth's algorithm D: U[0..UL] (UL + 2 words allocated, U[UL + 1] scratch) divided by P[0..t) (top word non-zero, t >= 1;
+// P is normalised in place and NOT restored).  On return Q[0..UL] holds the quotient and U[0..t) the remainder.
+ZKE_HD inline void bd_knuth_div(uint32_t* U, int UL, uint32_t* P, int t, uint32_t* Q) {
     // normalise so that the top bit of P[t-1] is set
     int s = 0;
     while (((P[t - 1] << s) & 0x80000000u) == 0) ++s;
@@ -147,6 +115,44 @@ ZKE_HD inline int fpmul_hint_words(uint32_t n, uint32_t k, const uint32_t* a_lim
     if (s) {
         for (int i = 0; i < t; ++i) U[i] = (U[i] >> s) | (i + 1 <= UL ? (U[i + 1] << (32 - s)) : 0);
     }
+}
+
+// a_limbs / b_limbs / p_limbs: k values of 8 words each (witness values).  q_out / r_out: k values of 8 words each.
+// Returns 0 on success, non-zero if the parameters exceed the supported size.
+ZKE_HD inline int fpmul_hint_words(uint32_t n, uint32_t k, const uint32_t* a_limbs, const uint32_t* b_limbs,
+                                   const uint32_t* p_limbs, uint32_t* q_out, uint32_t* r_out) {
+    const int W = (int)((n * k + 256 + 31) / 32);
+    if (W > BIGDIV_MAXW || n > 128 || n == 0) return 1;
+    uint32_t A[BIGDIV_MAXW], B[BIGDIV_MAXW], P[BIGDIV_MAXW + 1];
+    uint32_t U[2 * BIGDIV_MAXW + 2];   // dividend (normalised in place), ends up holding the remainder
+    uint32_t Q[2 * BIGDIV_MAXW + 1];
+    for (int i = 0; i < W; ++i) { A[i] = 0; B[i] = 0; P[i] = 0; }
+    for (uint32_t i = 0; i < k; ++i) {
+        bd_add_shifted(A, W, a_limbs + 8 * i, n * i);
+        bd_add_shifted(B, W, b_limbs + 8 * i, n * i);
+        bd_add_shifted(P, W, p_limbs + 8 * i, n * i);
+    }
+    const int UL = 2 * W;
+    for (int i = 0; i < UL + 2; ++i) U[i] = 0;
+    for (int i = 0; i < UL + 1; ++i) Q[i] = 0;
+    for (int i = 0; i < W; ++i) {
+        uint64_t carry = 0;
+        const uint64_t ai = A[i];
+        if (ai == 0) continue;
+        for (int j = 0; j < W; ++j) {
+            uint64_t s = ai * B[j] + U[i + j] + carry;
+            U[i + j] = (uint32_t)s;
+            carry = s >> 32;
+        }
+        U[i + W] = (uint32_t)carry;
+    }
+    int t = W;
+    while (t > 0 && P[t - 1] == 0) --t;
+    if (t == 0) {  // division by zero: circom's long_div would fail its own asserts; emit zeros, constraints reject
+        for (uint32_t i = 0; i < 8 * k; ++i) { q_out[i] = 0; r_out[i] = 0; }
+        return 0;
+    }
+    bd_knuth_div(U, UL, P, t, Q);
     for (int i = t; i < UL + 2; ++i) U[i] = 0;
     for (uint32_t i = 0; i < k; ++i) {
         bd_extract(Q, UL + 1, n * i, n, q_out + 8 * i);

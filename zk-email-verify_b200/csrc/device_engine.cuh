@@ -28,8 +28,9 @@ static const uint32_t WOP_NOP = 15;
 struct DevProgram {
     const uint4* ops;            // [n_iters][WITNESS_THREADS]
     const uint4* iter_hdr;       // [n_iters + 2]: {first term (even), term count (even), first cooperative op, their count}
-    const uint32_t* coop;        // cooperative ops of the iterations: offsets into `aux` of native Sha256compression tables
-                                 // ({n_desc, inputs[768], desc[n_desc][2]}, circuit.hpp: ShaBlock) - executed by the whole CTA
+    const uint32_t* coop;        // cooperative ops of the iterations (executed by the whole CTA), two words each:
+                                 // {offset into `aux`, 0}: native Sha256compression table ({n_desc, inputs[768],
+                                 // desc[n_desc][2]}, circuit.hpp: ShaBlock); {1 << 31 | offset into `aux`, dst}: FpMul hint
     const uint2* terms;
     const uint32_t* aux;
     const uint8_t* coef_r;       // [n_coefs][32]: coefficient * R mod r  (Montgomery-scaled: (cR) (x) w = c*w)

@@ -725,18 +725,21 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
             xlevel_ptr.swap(lp);
         }
         const uint32_t n_xlevels = xlevel_ptr.empty() ? 0 : (uint32_t)xlevel_ptr.size() - 1;
-        std::vector<uint32_t> coop;                     // cooperative ops, grouped by iteration
+        std::vector<uint32_t> coop;                     // cooperative ops (two words each), grouped by iteration
+        bool coop_fpmul = true;                         // ZKE_COOP_FPMUL=0: the sequential single-thread hint
+        if (const char* e = getenv("ZKE_COOP_FPMUL")) coop_fpmul = atoi(e) != 0;
         std::vector<uint32_t> order;
         std::vector<uint64_t> keys;
         for (uint32_t lvl = 0; lvl < n_xlevels; ++lvl) {
             const uint32_t beg = xlevel_ptr[lvl], end = xlevel_ptr[lvl + 1];
             order.clear();
-            const uint32_t coop_first = (uint32_t)coop.size();
+            const uint32_t coop_first = (uint32_t)(coop.size() / 2);
             for (uint32_t i = beg; i < end; ++i) {
-                if (xops[i].code == XOP_SHA) coop.push_back(sha_aux_off[xops[i].a]);
+                if (xops[i].code == XOP_SHA) { coop.push_back(sha_aux_off[xops[i].a]); coop.push_back(0); }
+                else if (xops[i].code == OP_FPMUL && coop_fpmul) { coop.push_back(0x80000000u | xops[i].a); coop.push_back(xops[i].dst); }
                 else order.push_back(i);
             }
-            uint32_t coop_left = (uint32_t)coop.size() - coop_first;   // attached to the level's first iteration
+            uint32_t coop_left = (uint32_t)(coop.size() / 2) - coop_first;   // attached to the level's first iteration
             // Sort key: kind, then the positions of the terms that need a product (coefficient other than +-1) in the
             // flattened [A | B | C] term list, then the term count.  Within an LC the product terms are emitted first
             // (addition commutes), so the ops of a warp take the product branch of eval_lcs in the same term slots -
@@ -816,7 +819,7 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         x->lc_terms.upload(terms);
         if (aux.empty()) aux.push_back(0);
         x->aux.upload(aux);
-        if (coop.empty()) coop.push_back(0);
+        if (coop.empty()) { coop.push_back(0); coop.push_back(0); }
         x->coop.upload(coop);
         const uint32_t NSMALL = 4096;
         std::vector<Fr> inv(NSMALL);

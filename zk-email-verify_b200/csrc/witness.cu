@@ -185,6 +185,141 @@ __device__ void sha_coop(const DevProgram& P, uint8_t* w, uint32_t aux_off, unsi
     __syncthreads();
 }
 
+// ---- cooperative FpMul hint ---------------------------------------------------------------------------------------
+// (q, r) = divmod(A * B, P) on 2048-bit integers.  The sequential Knuth division above costs ~0.66 ms per call in one
+// thread and the 17 chained calls of RSAVerifier65537 were a third of the witness kernel after the SHA substitution.
+// All of them share the modulus, so the CTA keeps Barrett's reciprocal mu = floor(b^(2t) / P) (b = 2^32, t = words of P)
+// in shared memory - computed once per email by the sequential division - and every call becomes three cooperative
+// products (column sums by 146 threads + one carry sweep): X = A B, q2 = floor(X / b^(t-1)) mu, q3 P, followed by at
+// most two corrective subtractions (Handbook of Applied Cryptography 14.42).  Falls back to the sequential routine when
+// the operands do not satisfy Barrett's preconditions (A, B >= b^t, or a modulus of fewer than four words).
+struct FpmulShared {
+    uint32_t A[BIGDIV_MAXW], B[BIGDIV_MAXW], P[BIGDIV_MAXW + 1];
+    uint32_t Pc[BIGDIV_MAXW + 1], mu[BIGDIV_MAXW + 2];     // cached modulus and its reciprocal
+    uint32_t X[2 * BIGDIV_MAXW + 2], q2[2 * BIGDIV_MAXW + 4], qp[2 * BIGDIV_MAXW + 4];
+    uint32_t Q[2 * BIGDIV_MAXW + 2], R[BIGDIV_MAXW + 2];
+    uint32_t lo[2 * BIGDIV_MAXW + 4], mid[2 * BIGDIV_MAXW + 4], hi[2 * BIGDIV_MAXW + 4];
+    int t, t_cached, mode;
+};
+
+// out[0 .. nx + ny) = x[0 .. nx) * y[0 .. ny), everything in shared memory; called by the whole CTA
+__device__ void coop_mul(uint32_t* out, const uint32_t* x, int nx, const uint32_t* y, int ny, FpmulShared& S) {
+    const int nc = nx + ny;
+    for (int c = threadIdx.x; c < nc; c += WITNESS_THREADS) {
+        unsigned long long acc = 0;
+        uint32_t top = 0;
+        const int i0 = c - (ny - 1) > 0 ? c - (ny - 1) : 0, i1 = c < nx - 1 ? c : nx - 1;
+        for (int i = i0; i <= i1; ++i) {
+            const unsigned long long pr = (unsigned long long)x[i] * y[c - i];
+            acc += pr;
+            top += acc < pr;
+        }
+        S.lo[c] = (uint32_t)acc; S.mid[c] = (uint32_t)(acc >> 32); S.hi[c] = top;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long carry = 0;
+        for (int c = 0; c < nc; ++c) {
+            const unsigned long long sum = carry + S.lo[c] + (c >= 1 ? S.mid[c - 1] : 0u) + (c >= 2 ? S.hi[c - 2] : 0u);
+            out[c] = (uint32_t)sum;
+            carry = sum >> 32;
+        }
+    }
+    __syncthreads();
+}
+
+__device__ void fpmul_coop(const DevProgram& P, uint8_t* w, uint32_t aux_off, uint32_t dst, FpmulShared& S) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t* ax = P.aux + aux_off;
+    const uint32_t n = ax[0], k = ax[1];
+    const int W = (int)((n * k + 256 + 31) / 32);
+    // assemble the three operands from their n-bit limbs (one thread each; 17 limbs x 9 words)
+    if (tid < 3) {
+        uint32_t* dstw = tid == 0 ? S.A : (tid == 1 ? S.B : S.P);
+        for (int i = 0; i < W; ++i) dstw[i] = 0;
+        for (uint32_t i = 0; i < k; ++i) {
+            const Fr x = Fr::load(w + 32ull * ax[2 + tid * k + i]);
+            bd_add_shifted(dstw, W, x.v, n * i);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int t = W;
+        while (t > 0 && S.P[t - 1] == 0) --t;
+        S.t = t;
+        bool fits = t >= 4;
+        for (int i = t; i < W && fits; ++i) fits = S.A[i] == 0 && S.B[i] == 0;       // A, B < b^t  =>  A B < b^(2t)
+        S.mode = fits ? 1 : 0;
+        if (fits) {
+            bool same = S.t_cached == t;
+            for (int i = 0; i < t && same; ++i) same = S.Pc[i] == S.P[i];
+            if (!same) {
+                // mu = floor(b^(2t) / P): sequential division, once per modulus (scratch: q2 = dividend, qp = divisor copy, X = quotient)
+                for (int i = 0; i < 2 * t + 2; ++i) S.q2[i] = 0;
+                S.q2[2 * t] = 1;
+                for (int i = 0; i < t; ++i) S.qp[i] = S.P[i];
+                for (int i = 0; i < 2 * t + 1; ++i) S.X[i] = 0;
+                bd_knuth_div(S.q2, 2 * t, S.qp, t, S.X);
+                if (S.X[t + 1] != 0) {            // P = b^(t-1) exactly: the reciprocal needs t + 2 words - sequential path
+                    S.mode = 0;
+                    S.t_cached = -1;
+                } else {
+                    for (int i = 0; i <= t; ++i) S.mu[i] = S.X[i];
+                    for (int i = 0; i < t; ++i) S.Pc[i] = S.P[i];
+                    S.t_cached = t;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (S.mode == 0) {
+        if (tid == 0) fpmul_hint_dev(P, w, aux_off, dst);          // sequential fallback (also t == 0: zeros)
+        __syncthreads();
+        return;
+    }
+    const int t = S.t;
+    coop_mul(S.X, S.A, t, S.B, t, S);                              // X = A B, 2t words
+    coop_mul(S.q2, S.X + (t - 1), t + 1, S.mu, t + 1, S);          // q1 mu, q1 = floor(X / b^(t-1))
+    coop_mul(S.qp, S.q2 + (t + 1), t + 1, S.P, t, S);              // q3 P,  q3 = floor(q2 / b^(t+1))
+    if (tid == 0) {
+        uint32_t* q3 = S.q2 + (t + 1);
+        // R = X - q3 P  (mod b^(t+1): 0 <= R < 3 P fits t + 1 words)
+        unsigned long long borrow = 0;
+        for (int i = 0; i <= t; ++i) {
+            const unsigned long long d = (unsigned long long)S.X[i] - S.qp[i] - borrow;
+            S.R[i] = (uint32_t)d;
+            borrow = (d >> 32) & 1;
+        }
+        for (int i = 0; i <= t; ++i) S.Q[i] = q3[i];
+        for (int i = t + 1; i < 2 * W + 1; ++i) S.Q[i] = 0;
+        for (int round = 0; round < 3; ++round) {                  // at most two corrections
+            bool ge = S.R[t] != 0;
+            if (!ge) {
+                ge = true;
+                for (int i = t - 1; i >= 0; --i) if (S.R[i] != S.P[i]) { ge = S.R[i] > S.P[i]; break; }
+            }
+            if (!ge) break;
+            unsigned long long br = 0;
+            for (int i = 0; i <= t; ++i) {
+                const unsigned long long d = (unsigned long long)S.R[i] - (i < t ? S.P[i] : 0u) - br;
+                S.R[i] = (uint32_t)d;
+                br = (d >> 32) & 1;
+            }
+            for (int i = 0; i <= t; ++i) { if (++S.Q[i] != 0) break; }
+        }
+        for (int i = t; i < W + 2; ++i) S.R[i] = 0;
+    }
+    __syncthreads();
+    if (tid < 2 * k) {
+        const uint32_t i = tid < k ? tid : tid - k;
+        Fr o;
+        if (tid < k) bd_extract(S.Q, 2 * W + 1, n * i, n, o.v);
+        else bd_extract(S.R, W + 2, n * i, n, o.v);
+        o.store(w + 32ull * (dst + tid));
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -210,6 +345,8 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
     uint2* const term_buf = reinterpret_cast<uint2*>(witness_smem);   // 2 x WITNESS_TERM_BUF
     __shared__ unsigned long long sha_q[SHA_Q_WORDS];
     __shared__ uint32_t sha_in[24];
+    __shared__ FpmulShared fpmul_s;
+    if (threadIdx.x == 0) fpmul_s.t_cached = -1;        // no reciprocal cached yet (ordered by the first barrier below)
     const uint32_t email = blockIdx.x;
     if (email >= batch) return;
     uint8_t* w = w_all + 32ull * stride_elems * email;
@@ -273,7 +410,11 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
         }
         // cooperative ops of this iteration (native Sha256compression): the whole CTA works on each in turn; they only
         // read signals of earlier levels and define signals nothing else in this iteration touches
-        for (uint32_t q = 0; q < hdr.w; ++q) sha_coop(P, w, P.coop[hdr.z + q], sha_q, sha_in);
+        for (uint32_t q = 0; q < hdr.w; ++q) {
+            const uint32_t c0 = P.coop[2 * (hdr.z + q)], c1 = P.coop[2 * (hdr.z + q) + 1];
+            if (c0 >> 31) fpmul_coop(P, w, c0 & 0x7fffffffu, c1, fpmul_s);
+            else sha_coop(P, w, c0, sha_q, sha_in);
+        }
         cp_async_wait_all();
         __syncthreads();     // level barrier and hand-over of the staged term block
         if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[k] = clock64();
