@@ -234,8 +234,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1 and args.impl == "b200":
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a bounded collective timeout: a rank that fails inside the optional extras must not hang the others for ever
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=600))
 
     circuit = z.Circuit(*CIRCUIT)
     info = circuit.info
@@ -391,7 +393,10 @@ def main():
     if not args.skip_extra_configs:
         ctx.close()
         del ctx, zk
-        other = extra_configs(z, torch, dist, rank, local_rank, world, key)
+        try:
+            other = extra_configs(z, torch, dist, rank, local_rank, world, key)
+        except Exception as e:          # the headline line must survive a failure of the optional measurements
+            other = {"extra_configs_error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
