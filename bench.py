@@ -201,8 +201,9 @@ def extra_configs(z, torch, dist, rank, local_rank, world, key):
                                     "bit_identical_to_single_gpu": same,
                                     "collectives": {"all_to_all_bytes_per_gpu_total": 6 * 32 * (n // world) * (world - 1) // world,
                                                     "all_gather_bytes_per_gpu": 388,
-                                                    "limiting": "no collective: the witness kernel is replicated (latency-bound, ~0.45 s of the total) and the proving "
-                                                                "part is a chain of short kernels with two host round trips between the three engine steps"}}
+                                                    "limiting": "no collective (each all-to-all moves < 60 MB per GPU over NVLink): the witness kernel is replicated "
+                                                                "(latency_ms - prove_only_latency_ms, a dependency chain more GPUs cannot shorten) and the proving part "
+                                                                "is a chain of short kernels with two host round trips between the three engine steps"}}
         ctx5.close()
         del ctx5, zk5
     return out

@@ -5,6 +5,7 @@
 //   mul_shoup       fixed-operand product (99 IMAD.WIDE + 16 IMAD)
 //   mul_cios+dfmaN  the same product stream with N independent DFMA per product in the same thread: if the FP64 pipe
 //                   ran beside the integer-multiply pipe, products/s would not move until the issue slots run out
+//   dfma68_only     the FP64 stream of the last row alone (68 DFMA per slot): the DFMA peak = slots/s x 68
 // Every thread keeps ILP independent chains x_k <- x_k * y; grids are one wave of `w` warps per scheduler.
 // Output: giga products per second (whole GPU) and the IMAD.WIDE rate that implies.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -I zk-email-verify_b200/csrc -o scripts/build/field_peaks scripts/field_peaks.cu
@@ -96,7 +97,8 @@ int main() {
     sweep<2, 0>("mul_shoup", 99, sms, out, false);
     sweep<0, 8>("mul_cios+dfma8", 136, sms, out, false);
     sweep<0, 32>("mul_cios+dfma32", 136, sms, out, false);
-    sweep<0, 68>("mul_cios+dfma68", 136, sms, out, true);
+    sweep<0, 68>("mul_cios+dfma68", 136, sms, out, false);
+    sweep<3, 68>("dfma68_only", 0, sms, out, true);     // the FP64 stream alone: 68 DFMA per "product" slot
     printf("}}\n");
     return 0;
 }
