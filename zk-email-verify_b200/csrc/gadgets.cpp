@@ -55,6 +55,7 @@ LC bits2num(Builder& b, const LCVec& bits) {
 
 LC is_zero(Builder& b, const LC& in_expr) {
     ScopeGuard g(b, "IsZero");
+    if (in_expr.is_const()) return in_expr.is_zero() ? one_lc() : LC();   // no hint variable for a compile-time constant
     LC in = b.signal(in_expr);
     Var inv = b.hint_invz(b.source_of(in));        // inv <-- in != 0 ? 1/in : 0
     LC out = b.mul_add(in.neg(), LC(inv), one_lc());   // out <== -in*inv + 1
