@@ -5,7 +5,8 @@ decomposed regex
 must set `out` exactly when the regex matches somewhere in the (zero-padded) message and reveal exactly the bytes of the
 bh= value.  The zk-regex package is un-vendored, so the pin is the regex itself: Python's `re` is the independent
 matcher the circuit's `out` is compared with - on curated headers and on a few hundred random strings over an alphabet
-that exercises every part of the automaton."""
+that exercises every part of the automaton.  Every test runs on both circuit shapes of the generator (regex.cpp): style 0,
+the zk-regex shape, and style 1, the compact shape (same function of the input, ~4x fewer constraints)."""
 import random
 import re
 
@@ -18,9 +19,9 @@ PATTERN = re.compile(rb"(\r\n|^)dkim-signature:([a-z]+=[^;]+; )+bh=([a-zA-Z0-9+/
 N = 128
 
 
-@pytest.fixture(scope="module")
-def circuit():
-    return z.Circuit("BodyHashRegex", [N])
+@pytest.fixture(scope="module", params=[0, 1], ids=["zkregex_shape", "compact_shape"])
+def circuit(request):
+    return z.Circuit("BodyHashRegex", [N, request.param])
 
 
 def _run(circuit, msg: bytes, n=N):
@@ -80,9 +81,10 @@ def test_reveal_feeds_select_regex_reveal(circuit):
     assert bytes(w.values("out")) == BH
 
 
-def test_body_hash_regex_out_agrees_with_python_re_on_random_strings():
+@pytest.mark.parametrize("style", [0, 1])
+def test_body_hash_regex_out_agrees_with_python_re_on_random_strings(style):
     n = 48
-    c = z.Circuit("BodyHashRegex", [n])
+    c = z.Circuit("BodyHashRegex", [n, style])
     rnd = random.Random(20260923)
     pieces = [b"dkim-signature:", b"\r\n", b"bh=", b"; ", b";", b"v=1", b"a=b", b"d=x.y", b"QUJD", b"+/=", b"=", b" ", b"Z", b"k", b":"]
     agree = hits = 0
@@ -131,6 +133,33 @@ def test_generic_regex_entry_point_matches_named_template():
     assert w.values("out") == [1] and bytes(b for b in w.values("reveal0") if b) == b"bob@mail.io"
     with pytest.raises(z._lib.ZkeError):
         z.Circuit.from_regex([("a*", True)], 8)          # matches the empty string
+
+
+def test_compact_shape_is_smaller_and_reveals_the_same():
+    """The two shapes are two circuits for one function: identical `out` / `reveal0` on inputs that include bytes >= 128,
+    the 255 marker value inside the message, overlapping partial matches and several matches."""
+    n = 96
+    zk, compact = z.Circuit("BodyHashRegex", [n, 0]), z.Circuit("BodyHashRegex", [n, 1])
+    assert compact.info.n_constraints * 3 < zk.info.n_constraints
+    rnd = random.Random(7)
+    base = b"\r\ndkim-signature:v=1; a=rsa-sha256; bh=QUJDREVG; b=x"
+    msgs = [base, base[2:], b"\xff" + base, base[:20] + b"\xff" + base[20:], base + base, b"dkim-signature:" + base,
+            "\r\ndkim-signature:v=1; d=\u00e9\u20ac\U0001f600; bh=QQ==; ".encode(), b"\r\ndkim-signature:v=1; d=\xc3\x28; bh=QQ==; ",
+            base.replace(b"; bh", b";  bh"), b"bh=QUJD;" * 8]
+    for _ in range(40):
+        m = bytearray(base)
+        for _k in range(rnd.randint(1, 4)):
+            m[rnd.randrange(len(m))] = rnd.choice([rnd.randrange(256), ord(";"), ord("="), ord(" "), 13, 10])
+        msgs.append(bytes(m))
+    for msg in msgs:
+        padded = list(msg[:n]) + [0] * (n - len(msg[:n]))
+        a, c2 = oracle_witness(zk, {"msg": padded}), oracle_witness(compact, {"msg": padded})
+        assert a.values("out") == c2.values("out") and a.values("reveal0") == c2.values("reveal0"), msg
+    tw0, tw1 = z.Circuit("TwitterResetRegex", [64, 0]), z.Circuit("TwitterResetRegex", [64, 1])
+    for msg in [b"x email was meant for @zk_mail.", b"email was meant for @", b"email was meant for @a email was meant for @bc!"]:
+        padded = list(msg) + [0] * (64 - len(msg))
+        a, c2 = oracle_witness(tw0, {"msg": padded}), oracle_witness(tw1, {"msg": padded})
+        assert a.values("out") == c2.values("out") and a.values("reveal0") == c2.values("reveal0"), msg
 
 
 @pytest.mark.gpu

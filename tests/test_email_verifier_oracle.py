@@ -125,3 +125,29 @@ def test_body_mask_variant():
     w = oracle_witness(c, inputs)
     body = [int(x) for x in inputs["emailBody"]]
     assert_out(w, {"maskedBody": body[:10] + [0] * 758})
+
+
+# ---- the compact regex shape inside EmailVerifier (regex.cpp, template parameter 10 = 1) -------------------------------
+def test_compact_regex_shape_variant(setup):
+    """Same statement, smaller circuit: identical public outputs on the same email, the tamper scenarios that go through
+    the body-hash regex still reject, and the default circuit drops below 2^21 constraints."""
+    _, dk, inputs = setup
+    c = Circuit("EmailVerifier", [640, 768, 121, 17, 0, 0, 0, 0, 1, 1])
+    ref = Circuit("EmailVerifier", [640, 768, 121, 17, 0, 0, 0, 0, 1, 0])
+    assert c.info.n_constraints < ref.info.n_constraints - 300_000
+    w, w0 = oracle_witness(c, inputs), oracle_witness(ref, inputs)
+    n_pub = 1 + c.info.n_public
+    assert w[:n_pub] == w0[:n_pub]
+    digest = hashlib.sha256(dk.headers).digest()
+    assert_out(w, {"shaHi": int.from_bytes(digest[:16], "big"), "shaLo": int.from_bytes(digest[16:], "big")})
+    bad = dict(inputs)
+    bad["bodyHashIndex"] = str(int(inputs["bodyHashIndex"]) + 1)           # email-verifier.test.ts:165-186
+    with pytest.raises(AssertFailed):
+        oracle_witness(c, bad)
+    hdr = list(inputs["emailHeader"])
+    pos = int(inputs["bodyHashIndex"]) - 2                                   # the '=' of "bh=": the regex no longer matches
+    hdr[pos] = str(ord("-"))
+    with pytest.raises(AssertFailed):
+        oracle_witness(c, dict(inputs, emailHeader=hdr))
+    full = Circuit("EmailVerifier", [1024, 1536, 121, 17, 0, 0, 0, 0, 0, 1])
+    assert full.info.domain_log2 == 21 and Circuit("EmailVerifier", [1024, 1536, 121, 17]).info.domain_log2 == 22

@@ -63,9 +63,13 @@ def test_rsa_and_fpmul():
 def test_regex_base64_reveal():
     n = 128
     hdr = b"to:a@b.c\r\ndkim-signature:v=1; a=rsa-sha256; bh=" + b"QUJD" * 10 + b"QUI=; b=xyz"
-    bh = check(z.Circuit("BodyHashRegex", [n]), {"msg": _pad(hdr, n)})
+    bh = check(z.Circuit("BodyHashRegex", [n, 0]), {"msg": _pad(hdr, n)})
     assert bh.get("IsZero", 0) > 0                            # character tests that hit their constant
-    check(z.Circuit("TwitterResetRegex", [64]), {"msg": _pad(b"x email was meant for @zk_mail.", 64)})
+    check(z.Circuit("TwitterResetRegex", [64, 0]), {"msg": _pad(b"x email was meant for @zk_mail.", 64)})
+    # the compact shape (one-hot live sets, nibble one-hots): nothing is free at all on a matching input
+    assert check(z.Circuit("BodyHashRegex", [n, 1]), {"msg": _pad(hdr, n)}) == {}
+    assert check(z.Circuit("TwitterResetRegex", [64, 1]), {"msg": _pad(b"x email was meant for @zk_mail.", 64)}) == {}
+    assert set(check(z.Circuit("BodyHashRegex", [n, 1]), {"msg": _pad(b"subject: nothing here", n)})) <= {"IsZero"}
     b64 = b"QUJD" * 10 + b"QUI="
     check(z.Circuit("Base64Decode", [32]), {"in": list(b64)})
     arr = [0] * 10 + list(b"hello") + [0] * 19

@@ -8,7 +8,8 @@
     proof; a context opened from the key alone proves a `.wtns` (snarkjs `groth16 prove zkey wtns`);
   * the pipelined submit / collect form of fullprove returns what the synchronous call returns;
   * externally supplied witnesses are validated;
-  * config 5 (EmailVerifier(1024, 16384), 2^24 domain) on one email - marked slow.
+  * config 5 (EmailVerifier(1024, 16384), 2^24 domain) on one email - marked slow;
+  * the compact regex shape (regex.cpp) inside EmailVerifier: witness and proof bit-exact against the oracle.
 """
 import ctypes
 import json
@@ -104,6 +105,43 @@ def test_email_verifier_proof_bit_exact_vs_oracle(ev):
     proof, pubs = z.proof_to_json(proofs, publics, c.info.n_public)
     assert z.verify(zk.vkey(), pubs, proof) and bn254.groth16_verify(zk.vkey(), pubs, proof)
     ctx.close()
+
+
+def test_compact_regex_shape_on_gpu(ev):
+    """EmailVerifier with the compact regex shape (template parameter 10 = 1): GPU witness == oracle witness, the proof
+    at fixed (r, s) == the CPU oracle's proof, same public signals as the zk-regex-shaped circuit, a header whose bh= tag
+    is broken is rejected; TwitterVerifier and BodyHashRegex alone in the same shape."""
+    c0, _, inputs = ev
+    c = z.Circuit("EmailVerifier", [640, 768, 121, 17, 0, 0, 0, 0, 1, 1])
+    assert c.info.n_constraints < c0.info.n_constraints - 300_000
+    zk = z.Zkey(c, seed=78, device=0)
+    ctx = z.Context(c, zk, device=0, max_batch=2)
+    hdr = list(inputs[1]["emailHeader"])
+    hdr[int(inputs[1]["bodyHashIndex"]) - 2] = str(ord("-"))
+    packed = c.pack_inputs(inputs[0]) + c.pack_inputs(dict(inputs[1], emailHeader=hdr))
+    wt, status = ctx.witness(packed, 2, raise_on_fail=False)
+    assert status[0] == -1 and status[1] >= 0
+    m = c.info.n_vars
+    ref = oracle_witness(c, inputs[0])
+    assert wt[:32 * m] == ref.raw()
+    proofs, publics, st = ctx.fullprove(c.pack_inputs(inputs[0]), 1, _rs(1))
+    assert st == [-1]
+    want = oracle_prove(c, product_sections(zk), wt[:32 * m], R_S[0], R_S[1], threads=16)
+    assert proofs == want
+    ref0 = oracle_witness(c0, inputs[0])
+    n_pub = c.info.n_public
+    assert publics == ref0.raw()[32:32 * (1 + n_pub)]
+    proof, pubs = z.proof_to_json(proofs, publics, n_pub)
+    assert z.verify(zk.vkey(), pubs, proof) and bn254.groth16_verify(zk.vkey(), pubs, proof)
+    ctx.close()
+    for name, params, msg in (("BodyHashRegex", [128, 1], b"\r\ndkim-signature:v=1; a=rsa-sha256; bh=QUJDREVG; b=x"),
+                              ("TwitterResetRegex", [64, 1], b"x email was meant for @zk_mail.")):
+        r = z.Circuit(name, params)
+        rctx = z.Context(r, None, device=0, max_batch=1)
+        padded = list(msg) + [0] * (params[0] - len(msg))
+        got, stt = rctx.witness(r.pack_inputs({"msg": padded}), 1)
+        assert stt == [-1] and got == oracle_witness(r, {"msg": padded}).raw()
+        rctx.close()
 
 
 # ------------------------------------------------------------------------------------------------ .zkey / .wtns drop-in

@@ -55,6 +55,7 @@ Circuit build_named(const std::string& name, const std::vector<int64_t>& p) {
         if (p.size() > 6) ep.enable_body_masking = p[6] != 0;
         if (p.size() > 7) ep.remove_soft_line_breaks = p[7] != 0;
         if (p.size() > 8) ep.public_pubkey = p[8] != 0;
+        if (p.size() > 9) ep.regex_style = (int)p[9];
         return build_email_verifier(ep);
     }
     if (name == "TwitterVerifier") {          // Proof-of-Twitter: EmailVerifier(H, Bd, n, k, 0) + body regex + packing + address
@@ -62,6 +63,7 @@ Circuit build_named(const std::string& name, const std::vector<int64_t>& p) {
         EmailVerifierParams ep;
         ep.max_headers_length = (uint32_t)p[0]; ep.max_body_length = (uint32_t)p[1]; ep.n = (uint32_t)p[2]; ep.k = (uint32_t)p[3];
         ep.twitter = true;
+        if (p.size() > 4) ep.regex_style = (int)p[4];
         return build_email_verifier(ep);
     }
     Builder b(name);
@@ -125,6 +127,7 @@ Circuit build_named(const std::string& name, const std::vector<int64_t>& p) {
         auto out = b.declare_outputs("out", 1);
         auto rev = b.declare_outputs("reveal0", n);
         LCVec msg = inputs(b, "msg", n);
+        if (p.size() > 1) b.regex_style = (int)p[1];
         LCVec r = twitter_reset_regex(b, msg);
         b.assign_output(out[0], r[0]);
         for (uint32_t i = 0; i < n; ++i) b.assign_output(rev[i], r[1 + i]);
@@ -184,6 +187,7 @@ Circuit build_named(const std::string& name, const std::vector<int64_t>& p) {
         auto out = b.declare_outputs("out", 1);
         auto rev = b.declare_outputs("reveal0", n);
         LCVec msg = inputs(b, "msg", n);
+        if (p.size() > 1) b.regex_style = (int)p[1];
         LCVec r = body_hash_regex(b, msg);
         b.assign_output(out[0], r[0]);
         for (uint32_t i = 0; i < n; ++i) b.assign_output(rev[i], r[1 + i]);

@@ -233,6 +233,11 @@ Var Builder::hint_fpmul(uint32_t n, uint32_t k, const std::vector<Var>& a, const
     return base;
 }
 
+int Builder::default_regex_style() {
+    const char* e = getenv("ZKE_REGEX_STYLE");
+    return e && atoi(e) == 1 ? 1 : 0;
+}
+
 bool Builder::default_fuse_shrand() {
     const char* e = getenv("ZKE_FUSED_SHRAND");
     return e ? atoi(e) != 0 : true;

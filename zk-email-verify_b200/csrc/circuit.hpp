@@ -165,6 +165,10 @@ class Builder {
     void pop_scope();
 
     bool materialize_linear = true;  // circom --O1 behaviour; false ~ --O2 (linear signals substituted)
+    // 0 = zk-regex circuit shape (comparators per range, OR of transitions), 1 = compact shape (regex.cpp); the same
+    // function of the input either way.  Default from ZKE_REGEX_STYLE; the named templates take it as a parameter.
+    int regex_style = default_regex_style();
+    static int default_regex_style();
     bool fuse_shrand = default_fuse_shrand();   // OP_SHRLC fusion in finalize() (ZKE_FUSED_SHRAND)
     static bool default_fuse_shrand();
 

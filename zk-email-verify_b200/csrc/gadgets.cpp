@@ -891,6 +891,7 @@ Circuit build_email_verifier(const EmailVerifierParams& P, bool materialize_line
         throw std::runtime_error("EmailVerifier: parameter asserts failed (email-verifier.circom:43-46)");
     Builder b("EmailVerifier");
     b.materialize_linear = materialize_linear;
+    if (P.regex_style >= 0) b.regex_style = P.regex_style;
     ScopeGuard g(b, "EmailVerifier");
 
     // outputs first (circom witness order)

@@ -90,6 +90,7 @@ struct EmailVerifierParams {
     // proof_of_twitter/public.json: [pubkeyHash, twitterUsername, address]): EmailVerifier as a sub-component whose
     // shaHi / shaLo stay internal, plus the body regex, PackRegexReveal(maxBodyLength, 21) and a public `address` input
     bool twitter = false;
+    int regex_style = -1;         // -1: Builder default (ZKE_REGEX_STYLE); 0 zk-regex shape; 1 compact shape (regex.cpp)
 };
 Circuit build_email_verifier(const EmailVerifierParams& p, bool materialize_linear = true);
 

@@ -10,6 +10,11 @@
 // live at every position (unanchored search), states[i+1][s] is the OR over incoming transitions of
 // (states[i][src] AND in[i] in class), out = OR_i states[i][accept], and reveal[i] = in[i] wherever a
 // transition of the public part fires (contract in SURVEY A.6).
+//
+// Builder::regex_style = 1 emits the same function of the input (same `out`, same `reveal0`) in a different circuit
+// shape ("compact", regex_circuit_compact below): character classes from nibble one-hots of a single bit decomposition per
+// byte instead of one 9-bit comparator per range end, and the live-state set itself as ONE one-hot state of the automaton
+// of live sets, so that a position costs one multiplication level and no OR gates.  ~3x fewer constraints.
 #include "gadgets.hpp"
 #include <algorithm>
 #include <array>
@@ -17,6 +22,10 @@
 #include <map>
 #include <set>
 #include <stdexcept>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <tuple>
 
 namespace zke {
 namespace gadgets {
@@ -323,6 +332,173 @@ static LCVec regex_circuit(Builder& b, const Dfa& dfa, const LCVec& msg) {
     return out;
 }
 
+// ------------------------------------------------------------------------------------------------ compact shape
+namespace {
+
+// The zk-regex shape keeps DFA state 0 live at every position, i.e. it runs one DFA thread per start position and the set
+// of live threads is what moves from byte to byte.  That set is itself the state of a deterministic automaton: from the
+// live set L and byte c the next set is {0} u {delta(s, c) : s in L}.  PowerDfa lists the reachable live sets (index 0 =
+// {0}), their transitions on bytes 0..254 (byte 255 is the `^` marker and matches nothing inside the message), whether a
+// public edge is taken by some thread, and whether the set holds an accepting DFA state.
+struct PowerDfa {
+    struct Tr { int src, dst; CharSet cs; bool pub; };
+    std::vector<std::vector<int>> members;
+    std::vector<bool> accept;
+    std::vector<Tr> trans;            // only transitions with dst != 0 ("every thread died" needs no product)
+    int after_marker = 0;             // live set after the 255 marker byte
+};
+
+PowerDfa build_power(const Dfa& dfa) {
+    const int S = dfa.n_states;
+    std::vector<std::array<int, 256>> delta(S);        // dst * 2 + pub, or -1
+    for (auto& row : delta) row.fill(-1);
+    for (auto& t : dfa.trans)
+        for (int c = 0; c < 256; ++c) if (t.cs.test(c)) delta[t.src][c] = t.dst * 2 + (t.pub ? 1 : 0);
+    PowerDfa pd;
+    std::map<std::vector<int>, int> index;
+    auto get = [&](std::vector<int> set) {
+        std::sort(set.begin(), set.end());
+        set.erase(std::unique(set.begin(), set.end()), set.end());
+        auto it = index.find(set);
+        if (it != index.end()) return it->second;
+        if (pd.members.size() >= 4096) throw std::runtime_error("regex: too many live-state sets for the compact circuit shape");
+        int id = (int)pd.members.size();
+        index[set] = id;
+        pd.members.push_back(set);
+        return id;
+    };
+    auto step = [&](const std::vector<int>& from, int c, bool& pub) {
+        std::vector<int> to{0};
+        pub = false;
+        for (int s : from) if (delta[s][c] >= 0) { to.push_back(delta[s][c] >> 1); pub = pub || (delta[s][c] & 1); }
+        return to;
+    };
+    get({0});
+    bool dummy;
+    pd.after_marker = get(step({0}, 255, dummy));
+    std::map<std::tuple<int, int, bool>, CharSet> grouped;
+    for (size_t li = 0; li < pd.members.size(); ++li) {
+        for (int c = 0; c < 255; ++c) {
+            bool pub;
+            const std::vector<int> from = pd.members[li];      // copy: get() may grow pd.members
+            int ti = get(step(from, c, pub));
+            if (ti != 0) grouped[std::make_tuple((int)li, ti, pub)].set(c);
+        }
+    }
+    pd.accept.resize(pd.members.size());
+    for (size_t li = 0; li < pd.members.size(); ++li) {
+        bool a = false;
+        for (int s : pd.members[li]) a = a || dfa.accept[s];
+        pd.accept[li] = a;
+    }
+    for (auto& kv : grouped) pd.trans.push_back(PowerDfa::Tr{std::get<0>(kv.first), std::get<1>(kv.first), kv.second, std::get<2>(kv.first)});
+    return pd;
+}
+
+// One-hot indicators of the two nibbles of a byte: 8 booleanity rows + 1 sum row (this IS the byte range check),
+// 2 + 15 products per nibble.
+struct ByteOneHot { LC lo[16], hi[16]; };
+
+ByteOneHot byte_one_hot(Builder& b, const LC& in) {
+    ScopeGuard g(b, "ByteOneHot");
+    const LC one = LC::constant(Fr::one());
+    LCVec bits = num2bits(b, in, 8);
+    ByteOneHot r;
+    for (int half = 0; half < 2; ++half) {
+        const LC* q = &bits[4 * half];
+        LC* out = half ? r.hi : r.lo;
+        LC p11 = b.mul(q[0], q[1]), r11 = b.mul(q[2], q[3]);
+        const LC p[4] = {one - q[0] - q[1] + p11, q[0] - p11, q[1] - p11, p11};      // index = q0 + 2 q1
+        const LC t[4] = {one - q[2] - q[3] + r11, q[2] - r11, q[3] - r11, r11};      // index = q2 + 2 q3
+        LC sum;
+        for (int j = 0; j < 15; ++j) { out[j] = b.mul(p[j & 3], t[j >> 2]); sum += out[j]; }
+        out[15] = one - sum;
+    }
+    return r;
+}
+
+// [byte in cs] as a linear combination of products (hi-nibble set) x (lo-nibble set); products are shared per position
+LC class_match(Builder& b, const ByteOneHot& oh, const CharSet& cs, std::map<std::pair<uint32_t, uint32_t>, LC>& cache) {
+    std::map<uint32_t, uint32_t> by_mask;        // lo-nibble mask -> set of hi nibbles that have exactly this mask
+    for (int h = 0; h < 16; ++h) {
+        uint32_t mask = 0;
+        for (int l = 0; l < 16; ++l) if (16 * h + l != 255 && cs.test(16 * h + l)) mask |= 1u << l;
+        if (mask) by_mask[mask] |= 1u << h;
+    }
+    LC m;
+    for (auto& kv : by_mask) {
+        LC hs;
+        for (int h = 0; h < 16; ++h) if (kv.second >> h & 1) hs += oh.hi[h];
+        if (kv.first == 0xffffu) { m += hs; continue; }
+        auto key = std::make_pair(kv.second, kv.first);
+        auto it = cache.find(key);
+        if (it == cache.end()) {
+            LC ls;
+            for (int l = 0; l < 16; ++l) if (kv.first >> l & 1) ls += oh.lo[l];
+            it = cache.emplace(key, b.mul(hs, ls)).first;
+        }
+        m += it->second;
+    }
+    return m;
+}
+
+LCVec regex_circuit_compact(Builder& b, const Dfa& dfa, const LCVec& msg) {
+    if (dfa.accept[0]) throw std::runtime_error("regex: matches the empty string");
+    const PowerDfa pd = build_power(dfa);
+    const int S = (int)pd.members.size();
+    if (getenv("ZKE_REGEX_DEBUG")) {
+        std::set<std::tuple<int, bool, std::string>> groups;
+        std::set<std::string> classes;
+        for (auto& t : pd.trans) { groups.insert(std::make_tuple(t.dst, t.pub, t.cs.to_string())); classes.insert(t.cs.to_string()); }
+        fprintf(stderr, "regex compact: %d DFA states, %d live sets, %zu transitions, %zu (dst, pub, class) groups, %zu classes\n",
+                dfa.n_states, S, pd.trans.size(), groups.size(), classes.size());
+    }
+    const LC one = LC::constant(Fr::one());
+    LCVec states(S);                       // exactly one of them is 1 at every position
+    states[pd.after_marker] = one;
+    LC accepted;                           // number of positions at which an accepting DFA state is live
+    auto count_accepts = [&]() { for (int s = 0; s < S; ++s) if (pd.accept[s] && !states[s].is_zero()) accepted += states[s]; };
+    count_accepts();
+    LCVec out(1 + msg.size());
+    for (size_t i = 0; i < msg.size(); ++i) {
+        const ByteOneHot oh = byte_one_hot(b, msg[i]);
+        std::map<std::pair<uint32_t, uint32_t>, LC> cache;
+        LCVec next(S);
+        LC reveal, moved;
+        // transitions that enter the same live set on the same class (and agree on `public`) share one product: the
+        // states are one-hot, so the sum of their sources is itself 0 / 1
+        std::map<std::tuple<int, bool, std::string>, std::pair<LC, const CharSet*>> groups;
+        for (auto& t : pd.trans) {
+            if (states[t.src].is_zero()) continue;                   // live set statically unreachable at this position
+            auto& gr = groups[std::make_tuple(t.dst, t.pub, t.cs.to_string())];
+            gr.first += states[t.src];
+            gr.second = &t.cs;
+        }
+        for (auto& kv : groups) {
+            LC m = class_match(b, oh, *kv.second.second, cache);
+            if (m.is_zero()) continue;
+            const LC& src = kv.second.first;
+            LC fire;
+            {
+                ScopeGuard g(b, "AND");
+                fire = src.is_const() ? m * src.const_value() : b.mul(src, m);
+            }
+            next[std::get<0>(kv.first)] += fire;
+            moved += fire;
+            if (std::get<1>(kv.first)) reveal += fire;
+        }
+        next[0] = one - moved;                                       // no transition fired: only the fresh thread is live
+        out[1 + i] = reveal.is_zero() ? LC() : b.mul(msg[i], reveal);   // reveal0[i] <== in[i] * is_reveal
+        states.swap(next);
+        count_accepts();
+    }
+    if (accepted.is_zero()) throw std::runtime_error("regex: accept state unreachable for this length");
+    out[0] = b.signal(one - is_zero(b, accepted));
+    return out;
+}
+
+}  // namespace
+
 LCVec body_hash_regex(Builder& b, const LCVec& msg) {
     ScopeGuard g(b, "BodyHashRegex");
     static const Dfa dfa = build_dfa({
@@ -331,13 +507,13 @@ LCVec body_hash_regex(Builder& b, const LCVec& msg) {
         {"[a-zA-Z0-9+/=]+", true},
         {";", false},
     });
-    return regex_circuit(b, dfa, msg);
+    return b.regex_style ? regex_circuit_compact(b, dfa, msg) : regex_circuit(b, dfa, msg);
 }
 
 LCVec regex_match(Builder& b, const std::string& scope, const std::vector<std::pair<std::string, bool>>& parts, const LCVec& msg) {
     ScopeGuard g(b, scope.c_str());
     const Dfa dfa = build_dfa(parts);
-    return regex_circuit(b, dfa, msg);
+    return b.regex_style ? regex_circuit_compact(b, dfa, msg) : regex_circuit(b, dfa, msg);
 }
 
 LCVec twitter_reset_regex(Builder& b, const LCVec& msg) {
@@ -346,7 +522,7 @@ LCVec twitter_reset_regex(Builder& b, const LCVec& msg) {
         {"email was meant for @", false},
         {"[a-zA-Z0-9_]+", true},
     });
-    return regex_circuit(b, dfa, msg);
+    return b.regex_style ? regex_circuit_compact(b, dfa, msg) : regex_circuit(b, dfa, msg);
 }
 
 }  // namespace gadgets
