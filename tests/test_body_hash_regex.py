@@ -135,6 +135,29 @@ def test_generic_regex_entry_point_matches_named_template():
         z.Circuit.from_regex([("a*", True)], 8)          # matches the empty string
 
 
+def test_generic_entry_point_in_the_compact_shape(monkeypatch):
+    """ZKE_REGEX_STYLE=1 selects the compact shape for zke_circuit_build_regex; alternation, optional parts, nested repeats
+    and a negated class behave as in the zk-regex shape and as Python's `re` says."""
+    cases = [([("to:", False), ("[a-z0-9.@]+", True), ("\r\n", False)], rb"to:([a-z0-9.@]+)\r\n",
+              [b"from:x\r\nto:bob@mail.io\r\n", b"to:\r\n", b"to:a\r\nto:bc\r\n", b"cc:bob\r\n"]),
+             ([("(ab|cd)+x?", False), ("[^ ]+", True), (" ", False)], rb"(?:ab|cd)+x?([^ ]+) ",
+              [b"abcdx12 ", b"zzabab9 z", b"ab ", b"cdxx y", b"ba x "]),
+             ([("id=", False), ("(0|[1-9][0-9]*)", True), (";", False)], rb"id=(0|[1-9][0-9]*);",
+              [b"id=0;", b"id=007;", b"xid=120;id=", b"id=;", b"id=12"])]
+    for parts, pattern, msgs in cases:
+        monkeypatch.setenv("ZKE_REGEX_STYLE", "0")
+        c0 = z.Circuit.from_regex(parts, 24)
+        monkeypatch.setenv("ZKE_REGEX_STYLE", "1")
+        c1 = z.Circuit.from_regex(parts, 24)
+        assert c1.info.n_constraints < c0.info.n_constraints
+        for msg in msgs:
+            padded = list(msg) + [0] * (24 - len(msg))
+            w0, w1 = oracle_witness(c0, {"msg": padded}), oracle_witness(c1, {"msg": padded})
+            m = re.search(pattern, bytes(padded))
+            assert w0.values("out") == w1.values("out") == [1 if m else 0], (parts, msg)
+            assert w0.values("reveal0") == w1.values("reveal0"), (parts, msg)
+
+
 def test_compact_shape_is_smaller_and_reveals_the_same():
     """The two shapes are two circuits for one function: identical `out` / `reveal0` on inputs that include bytes >= 128,
     the 255 marker value inside the message, overlapping partial matches and several matches."""
