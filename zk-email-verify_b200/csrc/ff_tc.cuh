@@ -1,0 +1,186 @@
+// Warp-collective Montgomery reduction on the tensor cores (sm_100a, legacy mma.sync IMMA path).
+//
+// Why: every heavy kernel of this engine is bound by the integer-multiply pipe, and 72 of the 136
+// IMAD.WIDE of a Montgomery product are the reduction - multiplications by CONSTANTS.  A reduction of a 512-bit
+// T = a * b is a linear map of the low half:
+//     T * 2^-256  ==  T_hi + sum_{j<32} t_j * C_j   (mod p),     t_j = byte j of T_lo,  C_j = 2^(8j - 256) mod p,
+// i.e. a (32 bytes) x (32 x 32 bytes) matrix product with a constant matrix: exactly an int8 tensor-core contraction.
+// One warp reduces its 32 elements (one per lane) with 2 x 4 mma.m16n8k32.u8 instructions; the column sums (< 2^21
+// each, byte-granular weights) are folded back into limbs on the ALU pipe, T_hi is added, and one 14-bit Barrett
+// step (1 IMAD.HI + 8 IMAD.WIDE) brings the 268-bit value into [0, 2p).  Multiplier instructions per product:
+// 64 + 9 instead of 136 (square: 36 + 9 instead of 108); the result is the same canonical a*b/2^256 mod p.
+//
+// Data movement: the rows of the A operand are the lanes' T_lo (2 x STS.128 per lane, 2 x ldmatrix.x4 per warp); the
+// columns of the constant matrix are permuted so that lane (g, t) of a quad ends up with the sums of bytes 8t .. 8t+7
+// of its four rows, folds them into three words, and hands them to the owner lane through shared memory.
+// All 32 lanes must call redc() convergently (mma.sync / ldmatrix are .aligned).
+//
+// Role in the reference: part of the Fr/Fq layer of wasmcurves 0.2.0 (un-vendored), see ff.cuh.
+#pragma once
+#include "ff.cuh"
+
+namespace zke {
+namespace dev {
+
+static const int TC_SCRATCH_WORDS = 640;     // per warp: 32 rows x 80 bytes (input rows use 48-byte strides of the same area)
+
+// Per-lane constants: the eight B-fragment registers of the reduction matrix (4 column tiles x 2 k-halves) and the
+// Barrett reciprocal floor(2^285 / p).  Built on the host by tc_build_table(); one table per field in global memory.
+struct TcTable {
+    uint32_t bfrag[32][8];
+    uint32_t mu;
+    uint32_t pad[7];
+};
+
+struct TcLane {
+    uint32_t b[8];
+    uint32_t mu;
+    uint32_t* scratch;     // this warp's TC_SCRATCH_WORDS words of shared memory (16-byte aligned)
+    __device__ __forceinline__ void init(const TcTable* tab, uint32_t* warp_scratch) {
+        const int lane = threadIdx.x & 31;
+        const uint4 lo = reinterpret_cast<const uint4*>(tab->bfrag[lane])[0], hi = reinterpret_cast<const uint4*>(tab->bfrag[lane])[1];
+        b[0] = lo.x; b[1] = lo.y; b[2] = lo.z; b[3] = lo.w; b[4] = hi.x; b[5] = hi.y; b[6] = hi.z; b[7] = hi.w;
+        mu = tab->mu;
+        scratch = warp_scratch;
+    }
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <class Tag>
+struct FpTc {
+    typedef Fp<Tag> F;
+
+    // T[0..16) -> T / 2^256 mod p, canonical.  Warp-collective.
+    static __device__ __forceinline__ F redc(const uint32_t* T, const TcLane& L) {
+        const FieldConsts& C = Tag::C();
+        const int lane = threadIdx.x & 31;
+        const int g = lane >> 2, t = lane & 3;
+        uint32_t* S = L.scratch;
+        __syncwarp();                                            // the previous call's hand-over rows have been read
+        {
+            uint4* row = reinterpret_cast<uint4*>(S + lane * 12);    // 48-byte row stride: conflict-free STS.128 / ldmatrix
+            row[0] = make_uint4(T[0], T[1], T[2], T[3]);
+            row[1] = make_uint4(T[4], T[5], T[6], T[7]);
+        }
+        __syncwarp();
+        // ldmatrix lane -> row address: matrix m = lane / 8 (m & 1: rows 8..15, m >> 1: bytes 16..31), row lane % 8
+        const uint32_t lm = smem_addr(S) + (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * 48 + (lane >> 4) * 16);
+        uint32_t a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(a[mt][0]), "=r"(a[mt][1]), "=r"(a[mt][2]), "=r"(a[mt][3]) : "r"(lm + mt * 16 * 48));
+        __syncwarp();                                            // every row is in registers: the area is reused below
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            int32_t d[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+                asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};"
+                             : "=r"(d[nt][0]), "=r"(d[nt][1]), "=r"(d[nt][2]), "=r"(d[nt][3])
+                             : "r"(a[mt][0]), "r"(a[mt][1]), "r"(a[mt][2]), "r"(a[mt][3]), "r"(L.b[2 * nt]), "r"(L.b[2 * nt + 1]), "r"(0));
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                // byte b = 2 nt + c of this lane's 8-byte slice of row 16 mt + 8 h + g is d[nt][2 h + c]
+                const uint32_t x01 = (uint32_t)d[0][2 * h] + ((uint32_t)d[0][2 * h + 1] << 8);
+                const uint32_t x23 = (uint32_t)d[1][2 * h] + ((uint32_t)d[1][2 * h + 1] << 8);
+                const uint32_t x45 = (uint32_t)d[2][2 * h] + ((uint32_t)d[2][2 * h + 1] << 8);
+                const uint32_t x67 = (uint32_t)d[3][2 * h] + ((uint32_t)d[3][2 * h + 1] << 8);
+                const uint32_t u_lo = add_cc(x01, x23 << 16), u_hi = addc(x23 >> 16, 0);
+                const uint32_t v_lo = add_cc(x45, x67 << 16), v_hi = addc(x67 >> 16, 0);
+                const uint32_t w1 = add_cc(u_hi, v_lo), w2 = addc(v_hi, 0);
+                *reinterpret_cast<uint4*>(S + (16 * mt + 8 * h + g) * 20 + t * 4) = make_uint4(u_lo, w1, w2, 0u);
+            }
+        }
+        __syncwarp();
+        uint32_t Lw[9];
+        {
+            const uint4* mine = reinterpret_cast<const uint4*>(S + lane * 20);
+            const uint4 p0 = mine[0], p1 = mine[1], p2 = mine[2], p3 = mine[3];
+            Lw[0] = p0.x; Lw[1] = p0.y;
+            Lw[2] = add_cc(p0.z, p1.x); Lw[3] = addc_cc(p1.y, 0);
+            Lw[4] = addc_cc(p1.z, p2.x); Lw[5] = addc_cc(p2.y, 0);
+            Lw[6] = addc_cc(p2.z, p3.x); Lw[7] = addc_cc(p3.y, 0);
+            Lw[8] = addc(p3.z, 0);
+        }
+        Lw[0] = add_cc(Lw[0], T[8]);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) Lw[k] = addc_cc(Lw[k], T[8 + k]);
+        Lw[8] = addc(Lw[8], 0);
+        // Barrett: q = floor(floor(r' / 2^240) * mu / 2^45) is the quotient digit or one below it: r' - q p in [0, 2p)
+        const uint32_t x = (Lw[8] << 16) | (Lw[7] >> 16);
+        const uint32_t q = __umulhi(x, L.mu) >> 13;
+        uint32_t od[8];
+        F::mul_n(od, C.nmod + 1, q);                            // limbs 1.. of q * (2^256 - p), odd positions
+        F::cmad_n(Lw, C.nmod, q);                               // even positions, on top of r'
+        F r;
+        r.v[0] = Lw[0];
+        r.v[1] = add_cc(Lw[1], od[0]);
+#pragma unroll
+        for (int k = 2; k < 7; ++k) r.v[k] = addc_cc(Lw[k], od[k - 1]);
+        r.v[7] = addc(Lw[7], od[6]);
+        r.reduce_once();
+        return r;
+    }
+
+    static __device__ __forceinline__ F mul(const F& a, const F& b, const TcLane& L) {
+        uint32_t T[16];
+        F::template mul_wide<8>(T, a.v, b.v);
+        return redc(T, L);
+    }
+    static __device__ __forceinline__ F sqr(const F& a, const TcLane& L) {
+        uint32_t T[16];
+        F::sqr_wide(T, a.v);
+        return redc(T, L);
+    }
+};
+
+#ifndef ZKE_FF_EMULATE
+// Host side: the constant matrix in fragment order.  mod = the field modulus, 8 little-endian limbs.
+// C_j = 2^(8j - 256) mod p by repeated halving from C_32 = 1; column `n` of tile `nt` holds byte 8 (n / 2) + 2 nt + (n & 1).
+inline void tc_build_table(const uint32_t* mod, TcTable* out) {
+    auto halve = [&](uint32_t* x) {
+        uint64_t carry = 0;
+        if (x[0] & 1) { for (int i = 0; i < 8; ++i) { carry += (uint64_t)x[i] + mod[i]; x[i] = (uint32_t)carry; carry >>= 32; } }
+        for (int i = 0; i < 8; ++i) x[i] = (x[i] >> 1) | (i < 7 ? x[i + 1] << 31 : (uint32_t)carry << 31);
+    };
+    uint8_t Cb[32][32];
+    uint32_t cur[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 31; j >= 0; --j) {
+        for (int h = 0; h < 8; ++h) halve(cur);
+        for (int k = 0; k < 32; ++k) Cb[j][k] = (uint8_t)(cur[k >> 2] >> (8 * (k & 3)));
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3;
+        for (int nt = 0; nt < 4; ++nt) {
+            const int byte = 8 * (g >> 1) + 2 * nt + (g & 1);
+            for (int half = 0; half < 2; ++half) {
+                uint32_t w = 0;
+                for (int i = 0; i < 4; ++i) w |= (uint32_t)Cb[16 * half + 4 * t + i][byte] << (8 * i);
+                out->bfrag[lane][2 * nt + half] = w;
+            }
+        }
+    }
+    // mu = floor(2^285 / p): long division of 2^285 by the top 96 bits is not exact enough; do it bit by bit on 9 limbs
+    uint32_t rem[10] = {0}, mu = 0;       // rem < p always
+    for (int bit = 285; bit >= 0; --bit) {
+        // rem = 2 rem + (bit == 285)
+        uint32_t c = bit == 285 ? 1u : 0u;
+        for (int i = 0; i < 9; ++i) { const uint32_t n = (rem[i] << 1) | c; c = rem[i] >> 31; rem[i] = n; }
+        // if rem >= p: rem -= p, quotient bit 1
+        bool ge = rem[8] != 0;
+        if (!ge) { ge = true; for (int i = 7; i >= 0; --i) if (rem[i] != mod[i]) { ge = rem[i] > mod[i]; break; } }
+        if (ge) {
+            uint64_t br = 0;
+            for (int i = 0; i < 9; ++i) { const uint64_t dd = (uint64_t)rem[i] - (i < 8 ? mod[i] : 0) - br; rem[i] = (uint32_t)dd; br = (dd >> 32) & 1; }
+            if (bit < 32) mu |= 1u << bit;
+        }
+    }
+    out->mu = mu;
+    for (int i = 0; i < 7; ++i) out->pad[i] = 0;
+}
+#endif
+
+}  // namespace dev
+}  // namespace zke
