@@ -36,5 +36,8 @@ for spec in sys.argv[1:] or ["lanes=8,split=1"]:
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / n
     print("%-40s %.1f ms/step  %.2f proofs/s" % (spec, dt * 1e3, BATCH / dt), flush=True)
+    if os.environ.get("SWEEP_PROFILE_EACH"):
+        ctx.profile(True); step(); prof = ctx.profile_get(); ctx.profile(False)
+        print("   ", {k: round(v["ms"] / max(1, v["count"]), 3) for k, v in prof.items()}, flush=True)
 ctx.profile(True); step(); prof = ctx.profile_get(); ctx.profile(False)
 print({k: round(v["ms"] / max(1, v["count"]), 3) for k, v in prof.items()})

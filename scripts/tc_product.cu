@@ -18,7 +18,7 @@ static const int ITERS = 2048;
 __device__ __forceinline__ uint32_t mix(uint32_t x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
 
 __global__ void __launch_bounds__(128) check(const TcTable* tab, uint32_t seed, uint32_t* mismatches, uint32_t* first_bad) {
-    __shared__ __align__(16) uint32_t scratch[4][TC_SCRATCH_WORDS];
+    __shared__ __align__(16) uint32_t scratch[4][2 * TC_SCRATCH_WORDS];
     TcLane L; L.init(tab, scratch[threadIdx.x >> 5]);
     const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
     Fq a, b;
@@ -33,7 +33,11 @@ __global__ void __launch_bounds__(128) check(const TcTable* tab, uint32_t seed, 
     for (int round = 0; round < 8; ++round) {
         const Fq want = Fq::mul_cios(a, b), got = FpTc<FqTag>::mul(a, b, L);
         const Fq want2 = Fq::sqr_cios(a), got2 = FpTc<FqTag>::sqr(a, L);
-        if (id != 3 && (want != got || want2 != got2)) { ++bad; if (atomicAdd(first_bad, 1u) == 0) first_bad[1] = id * 8 + round; }
+        Fq g3, g4, g5, g6;
+        FpTc<FqTag>::mul2(g3, g4, a, b, b, want2, L);
+        FpTc<FqTag>::sqr_mul(g5, g6, b, a, want2, L);
+        const bool pair_ok = g3 == want && g4 == Fq::mul_cios(b, want2) && g5 == Fq::sqr_cios(b) && g6 == Fq::mul_cios(a, want2);
+        if (id != 3 && (want != got || want2 != got2 || !pair_ok)) { ++bad; if (atomicAdd(first_bad, 1u) == 0) first_bad[1] = id * 8 + round; }
         a = got; b = want2;
     }
     if (bad) atomicAdd(mismatches, bad);
@@ -42,7 +46,7 @@ __global__ void __launch_bounds__(128) check(const TcTable* tab, uint32_t seed, 
 __device__ __forceinline__ int r_dummy(int k) { return k & 7; }
 template <int MODE>
 __global__ void __launch_bounds__(128) bench(const TcTable* tab, uint32_t* out, uint32_t seed) {
-    __shared__ __align__(16) uint32_t scratch[4][TC_SCRATCH_WORDS];
+    __shared__ __align__(16) uint32_t scratch[4][2 * TC_SCRATCH_WORDS];
     TcLane L; L.init(tab, scratch[threadIdx.x >> 5]);
     Fq x[ILP], y;
     for (int i = 0; i < 8; ++i) {
@@ -53,6 +57,8 @@ __global__ void __launch_bounds__(128) bench(const TcTable* tab, uint32_t* out, 
     for (int k = 0; k < ILP; ++k) x[k].v[7] &= 0x0fffffffu;
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
+        if (MODE == 8) { FpTc<FqTag>::mul2(x[0], x[1], x[0], y, x[1], y, L); continue; }      // two products per call
+        if (MODE == 9) { FpTc<FqTag>::sqr_mul(x[0], x[1], x[0], x[1], y, L); continue; }
 #pragma unroll
         for (int k = 0; k < ILP; ++k) {
             if (MODE == 0) x[k] = Fq::mul_cios(x[k], y);
@@ -145,6 +151,7 @@ int main(int argc, char** argv) {
         if (mode == 1) single<1>(tab, sms, bps, out);
         if (mode == 2) single<2>(tab, sms, bps, out);
         if (mode == 5) single<5>(tab, sms, bps, out);
+        if (mode == 8) single<8>(tab, sms, bps, out);
         return 0;
     }
     check<<<1024, 128>>>(tab, 12345u, mism, mism + 1);
@@ -163,7 +170,9 @@ int main(int argc, char** argv) {
     sweep<3>("mul_sos_plain", tab, sms, out, false);
     sweep<5>("redc_tc_only", tab, sms, out, false);
     sweep<6>("imma8_only", tab, sms, out, false);
-    sweep<7>("mul_wide_only", tab, sms, out, true);
+    sweep<7>("mul_wide_only", tab, sms, out, false);
+    sweep<8>("mul_tc_pair", tab, sms, out, false);
+    sweep<9>("sqr_mul_tc_pair", tab, sms, out, true);
     printf("}}\n");
     return h[0] ? 2 : 0;
 }

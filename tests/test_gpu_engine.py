@@ -226,6 +226,23 @@ def test_batched_affine_h_msm_bit_exact(levels, monkeypatch):
     assert proofs == oracle_prove(c, sec, wt, r, s, threads=8)
 
 
+@pytest.mark.parametrize("minb", ["3", "4", "5"])
+def test_tensor_core_reduction_h_msm_bit_exact(minb, monkeypatch):
+    """The opt-in bucket accumulation whose Montgomery reductions run on the tensor cores (ZKE_H_TC, msm_tc.cuh:
+    chunk_sum_tc_kernel, ff_tc.cuh) must give the proof the integer kernel and the CPU oracle give, bit for bit."""
+    from zkutil import oracle_prove, product_sections
+    monkeypatch.setenv("ZKE_H_TC", minb)
+    c = z.Circuit("Sha256Bytes", [64])
+    zk = z.Zkey(c, seed=3)
+    sec = product_sections(zk)
+    ctx = _ctx(c, zk)
+    padded, plen = z.sha256_pad(b"tensor-core reduction", 64)
+    wt, _ = ctx.witness(c.pack_inputs({"paddedIn": list(padded), "paddedInLength": plen}), 1)
+    r, s = 0x5555555555555555555555555555, 0x6666666666666666666666
+    proofs, _, _ = ctx.prove(1, r.to_bytes(32, "little") + s.to_bytes(32, "little"))
+    assert proofs == oracle_prove(c, sec, wt, r, s, threads=8)
+
+
 def test_witness_addon_templates():
     """RevealSubstring / CleanEmailAddress / CountSubstringOccurrences on the GPU witness kernel."""
     rs_in = [(i % 255) + 1 for i in range(100)] + [0] * 156

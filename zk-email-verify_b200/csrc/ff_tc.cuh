@@ -12,7 +12,8 @@
 //
 // Data movement: the rows of the A operand are the lanes' T_lo (2 x STS.128 per lane, 2 x ldmatrix.x4 per warp); the
 // columns of the constant matrix are permuted so that lane (g, t) of a quad ends up with the sums of bytes 8t .. 8t+7
-// of its four rows, folds them into three words, and hands them to the owner lane through shared memory.
+// of its four rows, folds them into three words, and hands them to the owner lanes with three stmatrix.x4 (the
+// fragment layout of stmatrix is exactly the transposition needed) - 40 shared-memory wavefronts per warp product.
 // All 32 lanes must call redc() convergently (mma.sync / ldmatrix are .aligned).
 //
 // Role in the reference: part of the Fr/Fq layer of wasmcurves 0.2.0 (un-vendored), see ff.cuh.
@@ -22,7 +23,7 @@
 namespace zke {
 namespace dev {
 
-static const int TC_SCRATCH_WORDS = 640;     // per warp: 32 rows x 80 bytes (input rows use 48-byte strides of the same area)
+static const int TC_SCRATCH_WORDS = 768;     // per warp and per simultaneous reduction: 32 input rows x 48 bytes, then three hand-over planes of 32 x 16 bytes
 
 // Per-lane constants: the eight B-fragment registers of the reduction matrix (4 column tiles x 2 k-halves) and the
 // Barrett reciprocal floor(2^285 / p).  Built on the host by tc_build_table(); one table per field in global memory.
@@ -46,82 +47,128 @@ struct TcLane {
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel)); return r; }
 
 template <class Tag>
 struct FpTc {
     typedef Fp<Tag> F;
 
-    // T[0..16) -> T / 2^256 mod p, canonical.  Warp-collective.
-    static __device__ __forceinline__ F redc(const uint32_t* T, const TcLane& L) {
+    // T[i][0..16) -> T[i] / 2^256 mod p, canonical, for NB independent values per lane.  Warp-collective.  NB = 2 gives
+    // the scheduler two independent dependency graphs between the two warp synchronisations (the column folding and the
+    // carry chains are latency-, not throughput-bound); the warp's scratch holds NB areas of TC_SCRATCH_WORDS words.
+    template <int NB>
+    static __device__ __forceinline__ void redc_n(F* r, const uint32_t (*T)[16], const TcLane& L) {
         const FieldConsts& C = Tag::C();
         const int lane = threadIdx.x & 31;
-        const int g = lane >> 2, t = lane & 3;
         uint32_t* S = L.scratch;
-        __syncwarp();                                            // the previous call's hand-over rows have been read
-        {
-            uint4* row = reinterpret_cast<uint4*>(S + lane * 12);    // 48-byte row stride: conflict-free STS.128 / ldmatrix
-            row[0] = make_uint4(T[0], T[1], T[2], T[3]);
-            row[1] = make_uint4(T[4], T[5], T[6], T[7]);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            uint4* row = reinterpret_cast<uint4*>(S + i * TC_SCRATCH_WORDS + lane * 12);    // 48-byte row stride: conflict-free STS.128 / ldmatrix
+            row[0] = make_uint4(T[i][0], T[i][1], T[i][2], T[i][3]);
+            row[1] = make_uint4(T[i][4], T[i][5], T[i][6], T[i][7]);
         }
         __syncwarp();
         // ldmatrix lane -> row address: matrix m = lane / 8 (m & 1: rows 8..15, m >> 1: bytes 16..31), row lane % 8
         const uint32_t lm = smem_addr(S) + (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * 48 + (lane >> 4) * 16);
-        uint32_t a[2][4];
+        // slot k = 2 mt + h <-> row 16 mt + 8 h + g = the element of lane 8 k + g; w[i][p][k]: word p of this lane's 8-byte slice
+        uint32_t w[NB][3][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
-            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(a[mt][0]), "=r"(a[mt][1]), "=r"(a[mt][2]), "=r"(a[mt][3]) : "r"(lm + mt * 16 * 48));
-        __syncwarp();                                            // every row is in registers: the area is reused below
+        for (int i = 0; i < NB; ++i) {
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            int32_t d[4][4];
+            for (int mt = 0; mt < 2; ++mt) {
+                uint32_t a[4];
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(lm + (uint32_t)(i * TC_SCRATCH_WORDS * 4 + mt * 16 * 48)) : "memory");
+                int32_t d[4][4];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
-                asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};"
-                             : "=r"(d[nt][0]), "=r"(d[nt][1]), "=r"(d[nt][2]), "=r"(d[nt][3])
-                             : "r"(a[mt][0]), "r"(a[mt][1]), "r"(a[mt][2]), "r"(a[mt][3]), "r"(L.b[2 * nt]), "r"(L.b[2 * nt + 1]), "r"(0));
+                for (int nt = 0; nt < 4; ++nt)
+                    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};"
+                                 : "=r"(d[nt][0]), "=r"(d[nt][1]), "=r"(d[nt][2]), "=r"(d[nt][3])
+                                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(L.b[2 * nt]), "r"(L.b[2 * nt + 1]), "r"(0));
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                // byte b = 2 nt + c of this lane's 8-byte slice of row 16 mt + 8 h + g is d[nt][2 h + c]
-                const uint32_t x01 = (uint32_t)d[0][2 * h] + ((uint32_t)d[0][2 * h + 1] << 8);
-                const uint32_t x23 = (uint32_t)d[1][2 * h] + ((uint32_t)d[1][2 * h + 1] << 8);
-                const uint32_t x45 = (uint32_t)d[2][2 * h] + ((uint32_t)d[2][2 * h + 1] << 8);
-                const uint32_t x67 = (uint32_t)d[3][2 * h] + ((uint32_t)d[3][2 * h + 1] << 8);
-                const uint32_t u_lo = add_cc(x01, x23 << 16), u_hi = addc(x23 >> 16, 0);
-                const uint32_t v_lo = add_cc(x45, x67 << 16), v_hi = addc(x67 >> 16, 0);
-                const uint32_t w1 = add_cc(u_hi, v_lo), w2 = addc(v_hi, 0);
-                *reinterpret_cast<uint4*>(S + (16 * mt + 8 * h + g) * 20 + t * 4) = make_uint4(u_lo, w1, w2, 0u);
+                for (int h = 0; h < 2; ++h) {
+                    // byte b = 2 nt + c of the slice is d[nt][2 h + c] (< 2^21); y_c = bytes 2c, 2c + 1 (< 2^30), value = sum y_c 2^(16 c).
+                    // The 16-bit shifts are byte permutes so that ptxas cannot turn them into IMAD.WIDE by 0x10000 (it did, for
+                    // a shift-and-add written in C or as add.cc / addc: 16 extra multiplier instructions per product).
+                    const uint32_t y0 = (uint32_t)d[0][2 * h] + ((uint32_t)d[0][2 * h + 1] << 8);
+                    const uint32_t y1 = (uint32_t)d[1][2 * h] + ((uint32_t)d[1][2 * h + 1] << 8);
+                    const uint32_t y2 = (uint32_t)d[2][2 * h] + ((uint32_t)d[2][2 * h + 1] << 8);
+                    const uint32_t y3 = (uint32_t)d[3][2 * h] + ((uint32_t)d[3][2 * h + 1] << 8);
+                    const uint32_t lo = prmt(y1, 0u, 0x1044u), mid = prmt(y1, y3, 0x5432u), hi = prmt(y3, 0u, 0x4432u);
+                    w[i][0][2 * mt + h] = add_cc(y0, lo);
+                    w[i][1][2 * mt + h] = addc_cc(y2, mid);
+                    w[i][2][2 * mt + h] = addc(hi, 0);
+                }
             }
         }
+        // hand-over: plane p, 16-byte row e = (word p of the four slices of element e), written in fragment order
+        const uint32_t out = smem_addr(S) + 1536u + (uint32_t)lane * 16u;
+#pragma unroll
+        for (int i = 0; i < NB; ++i)
+#pragma unroll
+            for (int p = 0; p < 3; ++p)
+                asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};"
+                             :: "r"(out + (uint32_t)(i * TC_SCRATCH_WORDS * 4 + p * 512)), "r"(w[i][p][0]), "r"(w[i][p][1]), "r"(w[i][p][2]), "r"(w[i][p][3]) : "memory");
         __syncwarp();
-        uint32_t Lw[9];
-        {
-            const uint4* mine = reinterpret_cast<const uint4*>(S + lane * 20);
-            const uint4 p0 = mine[0], p1 = mine[1], p2 = mine[2], p3 = mine[3];
-            Lw[0] = p0.x; Lw[1] = p0.y;
-            Lw[2] = add_cc(p0.z, p1.x); Lw[3] = addc_cc(p1.y, 0);
-            Lw[4] = addc_cc(p1.z, p2.x); Lw[5] = addc_cc(p2.y, 0);
-            Lw[6] = addc_cc(p2.z, p3.x); Lw[7] = addc_cc(p3.y, 0);
-            Lw[8] = addc(p3.z, 0);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            uint32_t Lw[9];
+            const uint4* mine = reinterpret_cast<const uint4*>(S + i * TC_SCRATCH_WORDS + 384 + lane * 4);
+            const uint4 p0 = mine[0], p1 = mine[32], p2 = mine[64];
+            Lw[0] = p0.x; Lw[1] = p1.x;
+            Lw[2] = add_cc(p2.x, p0.y); Lw[3] = addc_cc(p1.y, 0);
+            Lw[4] = addc_cc(p2.y, p0.z); Lw[5] = addc_cc(p1.z, 0);
+            Lw[6] = addc_cc(p2.z, p0.w); Lw[7] = addc_cc(p1.w, 0);
+            Lw[8] = addc(p2.w, 0);
+            Lw[0] = add_cc(Lw[0], T[i][8]);
+#pragma unroll
+            for (int k = 1; k < 8; ++k) Lw[k] = addc_cc(Lw[k], T[i][8 + k]);
+            Lw[8] = addc(Lw[8], 0);
+            // Barrett: q = floor(floor(r' / 2^240) * mu / 2^45) is the quotient digit or one below it: r' - q p in [0, 2p)
+            const uint32_t x = (Lw[8] << 16) | (Lw[7] >> 16);
+            const uint32_t q = __umulhi(x, L.mu) >> 13;
+            uint32_t od[8];
+            F::mul_n(od, C.nmod + 1, q);                            // limbs 1.. of q * (2^256 - p), odd positions
+            F::cmad_n(Lw, C.nmod, q);                               // even positions, on top of r'
+            r[i].v[0] = Lw[0];
+            r[i].v[1] = add_cc(Lw[1], od[0]);
+#pragma unroll
+            for (int k = 2; k < 7; ++k) r[i].v[k] = addc_cc(Lw[k], od[k - 1]);
+            r[i].v[7] = addc(Lw[7], od[6]);
+            r[i].reduce_once();
         }
-        Lw[0] = add_cc(Lw[0], T[8]);
-#pragma unroll
-        for (int k = 1; k < 8; ++k) Lw[k] = addc_cc(Lw[k], T[8 + k]);
-        Lw[8] = addc(Lw[8], 0);
-        // Barrett: q = floor(floor(r' / 2^240) * mu / 2^45) is the quotient digit or one below it: r' - q p in [0, 2p)
-        const uint32_t x = (Lw[8] << 16) | (Lw[7] >> 16);
-        const uint32_t q = __umulhi(x, L.mu) >> 13;
-        uint32_t od[8];
-        F::mul_n(od, C.nmod + 1, q);                            // limbs 1.. of q * (2^256 - p), odd positions
-        F::cmad_n(Lw, C.nmod, q);                               // even positions, on top of r'
+    }
+    static __device__ __forceinline__ F redc(const uint32_t* T, const TcLane& L) {
         F r;
-        r.v[0] = Lw[0];
-        r.v[1] = add_cc(Lw[1], od[0]);
-#pragma unroll
-        for (int k = 2; k < 7; ++k) r.v[k] = addc_cc(Lw[k], od[k - 1]);
-        r.v[7] = addc(Lw[7], od[6]);
-        r.reduce_once();
+        redc_n<1>(&r, reinterpret_cast<const uint32_t (*)[16]>(T), L);
         return r;
+    }
+    // (a*b, c*d): the two reductions share their synchronisation points
+    static __device__ __forceinline__ void mul2(F& r0, F& r1, const F& a, const F& b, const F& c, const F& d, const TcLane& L) {
+        uint32_t T[2][16];
+        F::template mul_wide<8>(T[0], a.v, b.v);
+        F::template mul_wide<8>(T[1], c.v, d.v);
+        F r[2];
+        redc_n<2>(r, T, L);
+        r0 = r[0]; r1 = r[1];
+    }
+    // (a^2, c^2)
+    static __device__ __forceinline__ void sqr2(F& r0, F& r1, const F& a, const F& c, const TcLane& L) {
+        uint32_t T[2][16];
+        F::sqr_wide(T[0], a.v);
+        F::sqr_wide(T[1], c.v);
+        F r[2];
+        redc_n<2>(r, T, L);
+        r0 = r[0]; r1 = r[1];
+    }
+    // (a^2, c*d)
+    static __device__ __forceinline__ void sqr_mul(F& r0, F& r1, const F& a, const F& c, const F& d, const TcLane& L) {
+        uint32_t T[2][16];
+        F::sqr_wide(T[0], a.v);
+        F::template mul_wide<8>(T[1], c.v, d.v);
+        F r[2];
+        redc_n<2>(r, T, L);
+        r0 = r[0]; r1 = r[1];
     }
 
     static __device__ __forceinline__ F mul(const F& a, const F& b, const TcLane& L) {

@@ -15,6 +15,9 @@
 #include "device_engine.cuh"
 #include "msm.cuh"
 #include "msm_ba.cuh"
+#if defined(ZKE_MSM_G1)
+#include "msm_tc.cuh"
+#endif
 #include <algorithm>
 #include <cstdlib>
 
@@ -662,7 +665,23 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
             int minb = sizeof(F) == 32 ? 5 : 4, waves = 4;
             if (const char* e = getenv("ZKE_CHUNK_MINB")) minb = atoi(e);
             if (const char* e = getenv("ZKE_CHUNK_WAVES")) waves = std::max(1, atoi(e));
-            if (minb >= 6) chunk_sum_kernel<F, 6><<<148 * 6 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
+            bool done = false;
+#if defined(ZKE_MSM_G1)
+            // ZKE_H_TC=1: Montgomery reductions of the bucket accumulation on the tensor cores (msm_tc.cuh), large G1 sets only
+            const char* h_tc_env = getenv("ZKE_H_TC");
+            const int h_tc = h_tc_env ? atoi(h_tc_env) : 0;
+            if (h_tc > 0 && cfg.precomputed) {
+                if (const TcTable* tab = tc_table_fq()) {
+                    const uint8_t* pts = reinterpret_cast<const uint8_t*>(points);
+                    if (h_tc >= 5) chunk_sum_tc_kernel<5><<<148 * 5 * waves, 128, 0, st>>>(pts, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial, tab);
+                    else if (h_tc == 4) chunk_sum_tc_kernel<4><<<148 * 4 * waves, 128, 0, st>>>(pts, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial, tab);
+                    else chunk_sum_tc_kernel<3><<<148 * 3 * waves, 128, 0, st>>>(pts, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial, tab);
+                    done = true;
+                }
+            }
+#endif
+            if (done) {}
+            else if (minb >= 6) chunk_sum_kernel<F, 6><<<148 * 6 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
             else if (minb == 5) chunk_sum_kernel<F, 5><<<148 * 5 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
             else chunk_sum_kernel<F, 4><<<148 * 4 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
         }
