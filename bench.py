@@ -363,6 +363,20 @@ def main():
     ms_e2e = timed(pinned_in.data_ptr(), args.steps)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    # ---- every proof of the last end-to-end batch is verified (outside the timed region): the batch verifier checks them
+    #      with one randomised product of pairings and falls back to one-by-one to name offenders
+    proofs_verified = None
+    if rank == 0:
+        try:
+            pr_raw, pb_raw = bytes(pinned_proofs.numpy()), bytes(pinned_pub.numpy())
+            t0 = time.perf_counter()
+            items = [z.proof_to_json(pr_raw[256 * k: 256 * (k + 1)], pb_raw[32 * npub * k: 32 * npub * (k + 1)], npub) for k in range(batch)]
+            oks = z.verify_batch(zk.vkey(), [it[1] for it in items], [it[0] for it in items])
+            proofs_verified = {"n": batch, "valid": int(sum(oks)), "status_ok": all(int(x) == -1 for x in status),
+                               "how": "zke_verify_batch_json: n + 3 Miller loops, one final exponentiation (host)",
+                               "ms": 1e3 * (time.perf_counter() - t0)}
+        except Exception as e:
+            proofs_verified = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     # ---- roofline pass: one extra step with per-stage CUDA events (single lane: no overlap, so the dominant kernel is
     #      timed alone on its launching stream); not part of `value`
     ctx.profile(True)
@@ -468,7 +482,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": len(packed),
                     "d2h_bytes_per_step": 256 * batch + 32 * npub * batch + 4 * batch},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "stage_ms": stages, "extra": extra,
+            "stage_ms": stages, "proofs_verified": proofs_verified, "extra": extra,
             "pipelining": "steps driven through zke_fullprove_submit/_collect, <= 2 batches in flight"}
     cc = (extra or {}).get("config2_compact_regex") if isinstance(extra, dict) else None
     if cc:

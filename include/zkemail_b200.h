@@ -226,6 +226,14 @@ int zke_shard_combine_raw(const uint8_t* key_points, const uint8_t* partials, in
  * ------------------------------------------------------------------------------------------------- */
 /* snarkjs.groth16.verify(vkey, publicSignals, proof): 1 valid, 0 invalid, < 0 malformed input.  Host only. */
 int zke_verify_json(const char* vkey_json, const char* public_json, const char* proof_json, char* err, size_t errcap);
+/* The same check for n proofs under ONE verification key ("batch Groth16 verification"; the reference
+ * verifies one proof per call: chunked-zkey.ts:93-105, rust-verifier/src/verifier_utils.rs:20): a random linear combination
+ * turns the 4n pairings into n + 3 Miller loops and one final exponentiation.  publics_json: array of n public-signal
+ * arrays, proofs_json: array of n proof objects; rand16: n x 16 bytes of caller randomness the provers cannot predict
+ * (NULL: std::random_device); ok (may be NULL): ok[i] = 1 / 0 - when the combined check fails the proofs are verified one
+ * by one to name the offenders.  Returns the number of valid proofs, < 0 on malformed input.  Host only. */
+int zke_verify_batch_json(const char* vkey_json, const char* publics_json, const char* proofs_json, const uint8_t* rand16,
+                          uint8_t* ok, char* err, size_t errcap);
 /* `snarkjs zkey export verificationkey`, incl. vk_alphabeta_12 = e(alpha_1, beta_2) in snarkjs' Fq12 tower layout
  * (/root/reference/packages/rust-verifier/tests/data/proof_of_twitter/vkey.json:43). */
 int zke_zkey_vkey_json(const zke_zkey* z, char* out, size_t* len);

@@ -134,6 +134,12 @@ def _prove_and_verify(circuit, inputs_list, seed=7):
             bad[0] = str((int(bad[0]) + 1) % z.FR_MODULUS)
             assert not bn254.groth16_verify(vkey, bad, proof)
         out.append((proof, pubs))
+    # the batch verifier (one randomised product of pairings) agrees, and names a tampered member
+    assert z.verify_batch(vkey, [o[1] for o in out], [o[0] for o in out]) == [True] * len(out)
+    if len(out) > 1 and out[0][1]:
+        bad = list(out[0][1])
+        bad[0] = str((int(bad[0]) + 1) % z.FR_MODULUS)
+        assert z.verify_batch(vkey, [bad] + [o[1] for o in out[1:]], [o[0] for o in out]) == [False] + [True] * (len(out) - 1)
     ctx.close()
     return out
 

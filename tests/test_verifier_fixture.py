@@ -87,3 +87,53 @@ def test_alphabeta_matches_reference_fixture():
     assert got == vkey["vk_alphabeta_12"]
     # malformed input: alpha off the curve
     assert L.zke_pairing_alphabeta(le(1) + le(1), beta, out) != 0
+
+
+# ---- batch verification (zke_verify_batch_json) -------------------------------------------------------
+R_ORDER = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+
+
+def _rerandomised(proof, k):
+    """Another valid proof of the same statement: (k A, k^-1 B, C) - e(kA, B / k) = e(A, B)."""
+    from oracle import bn254
+    a = bn254.g1_mul(bn254.g1_from_json(proof["pi_a"]), k)
+    b = bn254.g2_mul(bn254.g2_from_json(proof["pi_b"]), pow(k, -1, R_ORDER))
+    out = json.loads(json.dumps(proof))
+    out["pi_a"], out["pi_b"] = bn254.g1_to_json(a), bn254.g2_to_json(b)
+    return out
+
+
+def test_batch_verifier_accepts_distinct_valid_proofs_and_names_offenders():
+    vkey, public, proof = _load()
+    proofs = [proof, _rerandomised(proof, 7), _rerandomised(proof, 0x1234567890abcdef)]
+    assert proofs[1] != proof and z.verify(vkey, public, proofs[1]) is True
+    assert z.verify_batch(vkey, [public] * 3, proofs) == [True, True, True]
+    assert z.verify_batch(vkey, [public] * 3, proofs, rand=bytes(range(1, 49))) == [True, True, True]   # fixed randomness
+    assert z.verify_batch(vkey, [], []) == []
+    # one bad member: the combined check fails and the per-proof pass names it
+    bad = json.loads(json.dumps(proof))
+    bad["pi_c"][1] = str(Q - int(bad["pi_c"][1]))
+    assert z.verify_batch(vkey, [public] * 3, [proofs[0], bad, proofs[2]]) == [True, False, True]
+    bad_pub = list(public)
+    bad_pub[1] = str(int(bad_pub[1]) + 1)
+    assert z.verify_batch(vkey, [public, public, bad_pub], proofs) == [True, True, False]
+    # errors that cancel under equal weights are caught by the random ones: C_0 + D, C_1 - D
+    from oracle import bn254
+    d = bn254.g1_mul((1, 2), 5)
+    p0, p1 = json.loads(json.dumps(proof)), json.loads(json.dumps(proofs[1]))
+    p0["pi_c"] = bn254.g1_to_json(bn254.g1_add(bn254.g1_from_json(proof["pi_c"]), d))
+    p1["pi_c"] = bn254.g1_to_json(bn254.g1_add(bn254.g1_from_json(proofs[1]["pi_c"]), bn254.g1_neg(d)))
+    assert z.verify_batch(vkey, [public] * 2, [p0, p1]) == [False, False]
+
+
+def test_batch_verifier_malformed_input():
+    import pytest
+    vkey, public, proof = _load()
+    with pytest.raises(ValueError):
+        z.verify_batch(vkey, [public], [proof, proof])
+    with pytest.raises(ValueError):
+        z.verify_batch(vkey, [public], [proof], rand=b"short")
+    off = json.loads(json.dumps(proof))
+    off["pi_a"][0] = str(int(off["pi_a"][0]) + 1)          # off the curve: invalid, not an error
+    assert z.verify_batch(vkey, [public, public], [proof, off]) == [True, False]
+    assert z.verify_batch(vkey, [public[:-1]], [proof]) == [False]    # wrong number of public signals

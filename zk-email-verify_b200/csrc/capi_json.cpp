@@ -9,6 +9,7 @@
 #include "ec_host.hpp"
 #include <cstring>
 #include <memory>
+#include <random>
 
 using namespace zke;
 
@@ -199,6 +200,59 @@ int zke_verify_json(const char* vkey_json, const char* public_json, const char* 
         if (pub.type != JV::ARR) throw std::runtime_error("public signals must be an array");
         for (auto& s : pub.arr) publics.push_back(dec_of(s));
         return groth16_verify(k, publics, proof) ? 1 : 0;
+    } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
+}
+
+/* n proofs under one verification key: one randomised product of pairings (pairing_host.cpp: groth16_verify_batch); if it
+ * fails the proofs are checked one by one so that ok[i] names the offenders.  Returns the number of valid proofs. */
+int zke_verify_batch_json(const char* vkey_json, const char* publics_json, const char* proofs_json, const uint8_t* rand16,
+                          uint8_t* ok, char* err, size_t errcap) {
+    try {
+        if (!vkey_json || !publics_json || !proofs_json) throw std::runtime_error("null argument");
+        JV vk = JParser(vkey_json).parse(), pubs = JParser(publics_json).parse(), prs = JParser(proofs_json).parse();
+        const JV* prot = vk.get("protocol");
+        if (prot && prot->s != "groth16") throw std::runtime_error("vkey protocol is not groth16");
+        if (pubs.type != JV::ARR || prs.type != JV::ARR || pubs.arr.size() != prs.arr.size())
+            throw std::runtime_error("public signals and proofs must be arrays of the same length");
+        VerifyingKey k;
+        k.alpha1 = g1_of(need(vk, "vk_alpha_1"));
+        k.beta2 = g2_of(need(vk, "vk_beta_2"));
+        k.gamma2 = g2_of(need(vk, "vk_gamma_2"));
+        k.delta2 = g2_of(need(vk, "vk_delta_2"));
+        for (auto& p : need(vk, "IC").arr) k.ic.push_back(g1_of(p));
+        if (k.ic.empty()) throw std::runtime_error("vkey has no IC");
+        const size_t n = prs.arr.size();
+        std::vector<Proof> proofs(n);
+        std::vector<std::vector<U256>> publics(n);
+        std::vector<U256> rnd(n);
+        std::random_device rd;
+        for (size_t i = 0; i < n; ++i) {
+            const JV& pr = prs.arr[i];
+            const JV* pprot = pr.get("protocol");
+            if (pprot && pprot->s != "groth16") throw std::runtime_error("proof protocol is not groth16");
+            proofs[i].a = g1_of(need(pr, "pi_a"));
+            proofs[i].b = g2_of(need(pr, "pi_b"));
+            proofs[i].c = g1_of(need(pr, "pi_c"));
+            if (pubs.arr[i].type != JV::ARR) throw std::runtime_error("public signals must be an array per proof");
+            for (auto& s : pubs.arr[i].arr) publics[i].push_back(dec_of(s));
+            U256 r = {{0, 0, 0, 0}};
+            if (rand16) memcpy(r.v, rand16 + 16 * i, 16);
+            else { r.v[0] = ((uint64_t)rd() << 32) | rd(); r.v[1] = ((uint64_t)rd() << 32) | rd(); }
+            if (r.is_zero()) r.v[0] = 1;
+            rnd[i] = r;
+        }
+        int valid = 0;
+        if (groth16_verify_batch(k, publics, proofs, rnd)) {
+            for (size_t i = 0; i < n; ++i) if (ok) ok[i] = 1;
+            valid = (int)n;
+        } else {
+            for (size_t i = 0; i < n; ++i) {
+                const bool good = groth16_verify(k, publics[i], proofs[i]);
+                if (ok) ok[i] = good ? 1 : 0;
+                valid += good ? 1 : 0;
+            }
+        }
+        return valid;
     } catch (const std::exception& e) { set_err(err, errcap, e.what()); return -1; }
 }
 

@@ -146,6 +146,9 @@ struct Proof {
     G2AffineH b;
 };
 bool groth16_verify(const VerifyingKey& vk, const std::vector<U256>& publics, const Proof& pr);
+// n proofs under one key with one randomised product of pairings; rnd: n non-zero scalars below 2^128
+bool groth16_verify_batch(const VerifyingKey& vk, const std::vector<std::vector<U256>>& publics, const std::vector<Proof>& proofs,
+                          const std::vector<U256>& rnd);
 bool g2_in_subgroup(const G2AffineH& p);
 void pairing_alphabeta(const G1AffineH& alpha1, const G2AffineH& beta2, U256 out[12]);   // snarkjs vk_alphabeta_12, [i][j][k] flattened
 

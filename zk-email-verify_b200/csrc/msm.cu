@@ -680,10 +680,15 @@ void MsmPlan<F>::run(const uint8_t* points, const uint8_t* scalars, uint32_t n, 
                 }
             }
 #endif
+            // ZKE_CHUNK_PAD_SMEM=<bytes <= 48 K>: dynamic shared memory the kernel does not use - caps the resident blocks per SM
+            // below what the register file allows, so that blocks of the other lanes' (latency-bound) kernels find room
+            // beside a running bucket kernel (experiment; 0 = off)
+            size_t pad = 0;
+            if (const char* e = getenv("ZKE_CHUNK_PAD_SMEM")) pad = (size_t)std::max(0, std::min(48 * 1024, atoi(e)));
             if (done) {}
-            else if (minb >= 6) chunk_sum_kernel<F, 6><<<148 * 6 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
-            else if (minb == 5) chunk_sum_kernel<F, 5><<<148 * 5 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
-            else chunk_sum_kernel<F, 4><<<148 * 4 * waves, 128, 0, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
+            else if (minb >= 6) chunk_sum_kernel<F, 6><<<148 * 6 * waves, 128, pad, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
+            else if (minb == 5) chunk_sum_kernel<F, 5><<<148 * 5 * waves, 128, pad, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
+            else chunk_sum_kernel<F, 4><<<148 * 4 * waves, 128, pad, st>>>(points, entries, offsets, hist, chunk_off, work_bucket, order, n_buckets, D.chunk, partial);
         }
         if (ev) cudaEventRecord(ev[1], st);
         if (st != st_light) {

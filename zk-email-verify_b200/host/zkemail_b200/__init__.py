@@ -9,7 +9,7 @@ from .dkim import DKIMVerificationResult, verify_dkim_signature  # noqa: F401
 from .input_generators import (generate_circuit_inputs, generate_email_verifier_inputs,  # noqa: F401
                                generate_twitter_verifier_inputs_from_dkim_result,
                                generate_email_verifier_inputs_from_dkim_result)
-from .engine import AssertFailed, Context, Zkey, device_count, proof_to_json, verify  # noqa: F401
+from .engine import AssertFailed, Context, Zkey, device_count, proof_to_json, verify, verify_batch  # noqa: F401
 from .chunked_zkey import (generate_proof, verify_proof, register_circuit, register_zkey_files, generateProof, verifyProof,  # noqa: F401
                            InsecureKeyError)
 from . import synthetic  # noqa: F401,E402

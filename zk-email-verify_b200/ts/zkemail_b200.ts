@@ -13,6 +13,7 @@ const zke_ctx_open = lib.func('void* zke_ctx_open(void*, void*, int, uint32_t, c
 const zke_zkey_vkey_json = lib.func('int zke_zkey_vkey_json(void*, char*, size_t*)');
 const zke_fullprove_json = lib.func('int zke_fullprove_json(void*, void*, const char*, char*, size_t*, char*, size_t*, char*, size_t)');
 const zke_verify_json = lib.func('int zke_verify_json(const char*, const char*, const char*, char*, size_t)');
+const zke_verify_batch_json = lib.func('int zke_verify_batch_json(const char*, const char*, const char*, const uint8_t*, uint8_t*, char*, size_t)');
 
 const cstr = (b: Buffer) => b.toString('utf8', 0, b.indexOf(0));
 type Entry = { circuit: unknown; zkey: unknown; ctx: unknown };
@@ -75,5 +76,13 @@ export const groth16 = {
     const rc = zke_verify_json(JSON.stringify(vkey), JSON.stringify(publicSignals), JSON.stringify(proof), err, err.length);
     if (rc < 0) throw new Error(cstr(err));
     return rc === 1;
+  },
+  /** n proofs under one key with one randomised product of pairings; per-proof verdicts (not in snarkjs) */
+  async verifyBatch(vkey: object, publicSignals: string[][], proofs: object[]): Promise<boolean[]> {
+    const err = Buffer.alloc(4096), ok = Buffer.alloc(proofs.length);
+    const rand = require('crypto').randomBytes(16 * proofs.length);
+    const rc = zke_verify_batch_json(JSON.stringify(vkey), JSON.stringify(publicSignals), JSON.stringify(proofs), rand, ok, err, err.length);
+    if (rc < 0) throw new Error(cstr(err));
+    return Array.from(ok).map((b) => b === 1);
   },
 };
