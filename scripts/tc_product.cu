@@ -36,6 +36,11 @@ __global__ void __launch_bounds__(128) check(const TcTable* tab, uint32_t seed, 
         Fq g3, g4, g5, g6;
         FpTc<FqTag>::mul2(g3, g4, a, b, b, want2, L);
         FpTc<FqTag>::sqr_mul(g5, g6, b, a, want2, L);
+        uint32_t Ta[16], Tb[16];
+        Fq::mul_wide<8>(Ta, a.v, b.v);
+        const Fq g7 = FpTc<FqTag>::redc_mul(Ta, Tb, b, want2, L);        // a*b reduced while b*want2 is formed
+        const Fq g8 = FpTc<FqTag>::redc(Tb, L);
+        if (id != 3 && (g7 != want || g8 != Fq::mul_cios(b, want2))) { ++bad; if (atomicAdd(first_bad, 1u) == 0) first_bad[1] = 0x80000000u | (id * 8 + round); }
         const bool pair_ok = g3 == want && g4 == Fq::mul_cios(b, want2) && g5 == Fq::sqr_cios(b) && g6 == Fq::mul_cios(a, want2);
         if (id != 3 && (want != got || want2 != got2 || !pair_ok)) { ++bad; if (atomicAdd(first_bad, 1u) == 0) first_bad[1] = id * 8 + round; }
         a = got; b = want2;
@@ -55,8 +60,15 @@ __global__ void __launch_bounds__(128) bench(const TcTable* tab, uint32_t* out, 
     }
     y.v[7] &= 0x0fffffffu;
     for (int k = 0; k < ILP; ++k) x[k].v[7] &= 0x0fffffffu;
+    uint32_t Tw[2][16];
+    if (MODE == 10) Fq::mul_wide<8>(Tw[0], x[0].v, y.v);
 #pragma unroll 1
     for (int it = 0; it < ITERS; ++it) {
+        if (MODE == 10) {       // software-pipelined: the reduction of one chain's product under the rows of the other chain's
+            x[0] = FpTc<FqTag>::redc_mul(Tw[0], Tw[1], x[1], y, L);
+            x[1] = FpTc<FqTag>::redc_mul(Tw[1], Tw[0], x[0], y, L);
+            continue;
+        }
         if (MODE == 8) { FpTc<FqTag>::mul2(x[0], x[1], x[0], y, x[1], y, L); continue; }      // two products per call
         if (MODE == 9) { FpTc<FqTag>::sqr_mul(x[0], x[1], x[0], x[1], y, L); continue; }
 #pragma unroll
@@ -152,6 +164,7 @@ int main(int argc, char** argv) {
         if (mode == 2) single<2>(tab, sms, bps, out);
         if (mode == 5) single<5>(tab, sms, bps, out);
         if (mode == 8) single<8>(tab, sms, bps, out);
+        if (mode == 10) single<10>(tab, sms, bps, out);
         return 0;
     }
     check<<<1024, 128>>>(tab, 12345u, mism, mism + 1);
@@ -172,7 +185,8 @@ int main(int argc, char** argv) {
     sweep<6>("imma8_only", tab, sms, out, false);
     sweep<7>("mul_wide_only", tab, sms, out, false);
     sweep<8>("mul_tc_pair", tab, sms, out, false);
-    sweep<9>("sqr_mul_tc_pair", tab, sms, out, true);
+    sweep<9>("sqr_mul_tc_pair", tab, sms, out, false);
+    sweep<10>("mul_tc_pipelined", tab, sms, out, true);
     printf("}}\n");
     return h[0] ? 2 : 0;
 }

@@ -138,6 +138,117 @@ struct FpTc {
             r[i].reduce_once();
         }
     }
+    // ---- software-pipelined form: r = redc(Tp) while the NEXT 512-bit product Tn = a * b is formed by the same warp.
+    // The reduction is a latency chain (store, ldmatrix, IMMA, fold, stmatrix, load, carry chains) on the shared-memory,
+    // tensor and ALU pipes; the schoolbook product is 64 back-to-back IMAD.WIDE.  Run one after the other, the warps of a
+    // scheduler convoy: all of them queue for the multiplier, then all of them wait out the reduction.  Here the eight
+    // rows of the product are issued between the steps of the reduction, so every warp always has both kinds of work in
+    // flight.  Tn must not depend on the result r (the caller alternates between independent values).
+    struct WideRows {
+        uint32_t ev[16], od[16];     // od[k] sits at limb position k + 1
+        int ee, eo;
+        __device__ __forceinline__ WideRows() : ee(0), eo(0) {}
+        template <int I>
+        __device__ __forceinline__ void row(const uint32_t* a, uint32_t bi) {
+            if ((I & 1) == 0) {
+                ee = F::template chain<4>(ev, ee, I, a, 0, 2, bi);
+                eo = F::template chain<4>(od, eo, I, a, 1, 2, bi);
+            } else {
+                eo = F::template chain<4>(od, eo, I - 1, a, 0, 2, bi);
+                ee = F::template chain<4>(ev, ee, I + 1, a, 1, 2, bi);
+            }
+        }
+        __device__ __forceinline__ void finish(uint32_t* T) const {
+            T[0] = ev[0];
+            T[1] = add_cc(ev[1], od[0]);
+#pragma unroll
+            for (int k = 2; k < 16; ++k) {
+                const uint32_t e = k < ee ? ev[k] : 0, o = (k - 1) < eo ? od[k - 1] : 0;
+                T[k] = k + 1 < 16 ? addc_cc(e, o) : addc(e, o);
+            }
+        }
+    };
+    static __device__ __forceinline__ F redc_mul(const uint32_t* Tp, uint32_t* Tn, const F& a, const F& b, const TcLane& L) {
+        const FieldConsts& C = Tag::C();
+        const int lane = threadIdx.x & 31;
+        uint32_t* S = L.scratch;
+        WideRows W;
+        {
+            uint4* row = reinterpret_cast<uint4*>(S + lane * 12);
+            row[0] = make_uint4(Tp[0], Tp[1], Tp[2], Tp[3]);
+            row[1] = make_uint4(Tp[4], Tp[5], Tp[6], Tp[7]);
+        }
+        W.template row<0>(a.v, b.v[0]);
+        W.template row<1>(a.v, b.v[1]);
+        __syncwarp();
+        const uint32_t lm = smem_addr(S) + (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * 48 + (lane >> 4) * 16);
+        uint32_t af[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(af[mt][0]), "=r"(af[mt][1]), "=r"(af[mt][2]), "=r"(af[mt][3]) : "r"(lm + (uint32_t)(mt * 16 * 48)) : "memory");
+        W.template row<2>(a.v, b.v[2]);
+        W.template row<3>(a.v, b.v[3]);
+        uint32_t w[3][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            int32_t d[4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+                asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%10, %10, %10, %10};"
+                             : "=r"(d[nt][0]), "=r"(d[nt][1]), "=r"(d[nt][2]), "=r"(d[nt][3])
+                             : "r"(af[mt][0]), "r"(af[mt][1]), "r"(af[mt][2]), "r"(af[mt][3]), "r"(L.b[2 * nt]), "r"(L.b[2 * nt + 1]), "r"(0));
+            if (mt == 0) W.template row<4>(a.v, b.v[4]); else W.template row<5>(a.v, b.v[5]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t y0 = (uint32_t)d[0][2 * h] + ((uint32_t)d[0][2 * h + 1] << 8);
+                const uint32_t y1 = (uint32_t)d[1][2 * h] + ((uint32_t)d[1][2 * h + 1] << 8);
+                const uint32_t y2 = (uint32_t)d[2][2 * h] + ((uint32_t)d[2][2 * h + 1] << 8);
+                const uint32_t y3 = (uint32_t)d[3][2 * h] + ((uint32_t)d[3][2 * h + 1] << 8);
+                const uint32_t lo = prmt(y1, 0u, 0x1044u), mid = prmt(y1, y3, 0x5432u), hi = prmt(y3, 0u, 0x4432u);
+                w[0][2 * mt + h] = add_cc(y0, lo);
+                w[1][2 * mt + h] = addc_cc(y2, mid);
+                w[2][2 * mt + h] = addc(hi, 0);
+            }
+        }
+        const uint32_t out = smem_addr(S) + 1536u + (uint32_t)lane * 16u;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+            asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};"
+                         :: "r"(out + (uint32_t)(p * 512)), "r"(w[p][0]), "r"(w[p][1]), "r"(w[p][2]), "r"(w[p][3]) : "memory");
+        W.template row<6>(a.v, b.v[6]);
+        W.template row<7>(a.v, b.v[7]);
+        __syncwarp();
+        uint32_t Lw[9];
+        {
+            const uint4* mine = reinterpret_cast<const uint4*>(S + 384 + lane * 4);
+            const uint4 p0 = mine[0], p1 = mine[32], p2 = mine[64];
+            W.finish(Tn);                                          // the merge of the new product covers the load latency
+            Lw[0] = p0.x; Lw[1] = p1.x;
+            Lw[2] = add_cc(p2.x, p0.y); Lw[3] = addc_cc(p1.y, 0);
+            Lw[4] = addc_cc(p2.y, p0.z); Lw[5] = addc_cc(p1.z, 0);
+            Lw[6] = addc_cc(p2.z, p0.w); Lw[7] = addc_cc(p1.w, 0);
+            Lw[8] = addc(p2.w, 0);
+        }
+        Lw[0] = add_cc(Lw[0], Tp[8]);
+#pragma unroll
+        for (int k = 1; k < 8; ++k) Lw[k] = addc_cc(Lw[k], Tp[8 + k]);
+        Lw[8] = addc(Lw[8], 0);
+        const uint32_t x = (Lw[8] << 16) | (Lw[7] >> 16);
+        const uint32_t q = __umulhi(x, L.mu) >> 13;
+        uint32_t od[8];
+        F::mul_n(od, C.nmod + 1, q);
+        F::cmad_n(Lw, C.nmod, q);
+        F r;
+        r.v[0] = Lw[0];
+        r.v[1] = add_cc(Lw[1], od[0]);
+#pragma unroll
+        for (int k = 2; k < 7; ++k) r.v[k] = addc_cc(Lw[k], od[k - 1]);
+        r.v[7] = addc(Lw[7], od[6]);
+        r.reduce_once();
+        return r;
+    }
+
     static __device__ __forceinline__ F redc(const uint32_t* T, const TcLane& L) {
         F r;
         redc_n<1>(&r, reinterpret_cast<const uint32_t (*)[16]>(T), L);
