@@ -85,9 +85,13 @@ enum {
     ZKE_ARR_LC_PTR = 12, ZKE_ARR_LC_VAR = 13, ZKE_ARR_LC_COEF = 14, /* LC pool of the witness program */
     ZKE_ARR_AUX = 15,       /* uint32 operands of OP_FPMUL                                            */
     ZKE_ARR_SCOPE_OF_CONSTRAINT = 16, /* uint16[n_constraints]                                        */
-    ZKE_ARR_SHA_BLOCKS = 17 /* uint32: {n_blocks, per block: var_begin, var_end, temp_begin, temp_end, n_desc,
+    ZKE_ARR_SHA_BLOCKS = 17, /* uint32: {n_blocks, per block: var_begin, var_end, temp_begin, temp_end, n_desc,
                                inputs[768], desc[n_desc][2] = {signal, quantity << 8 | bit}} - the Sha256compression
                                instances the engine evaluates natively (one compression instead of ~320 levels)  */
+    ZKE_ARR_REGEX_SEEDS = 18 /* uint32: {n_seeds, per seed: n_desc, n_bytes, n_states, first_mask lo, hi, bytes[n_bytes]
+                               (signal of message byte j), table[n_states * 64] (destination state of (source, byte),
+                               0xff = none, 4 per word), desc[n_desc][2] = {signal, position << 8 | state}} - the zk-regex
+                               instances whose state signals the engine seeds with one automaton run               */
 };
 const void* zke_circuit_array(const zke_circuit* c, int which, size_t* n_elems);
 const char* zke_circuit_scope_name(const zke_circuit* c, uint32_t scope_index);

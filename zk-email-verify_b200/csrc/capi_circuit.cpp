@@ -348,6 +348,7 @@ const void* zke_circuit_array(const zke_circuit* c, int which, size_t* n) {
         case ZKE_ARR_AUX: RET(k.aux);
         case ZKE_ARR_SCOPE_OF_CONSTRAINT: RET(k.scope_of_constraint);
         case ZKE_ARR_SHA_BLOCKS: RET(k.sha_flat);
+        case ZKE_ARR_REGEX_SEEDS: RET(k.regex_flat);
         default: *n = 0; return nullptr;
     }
 #undef RET

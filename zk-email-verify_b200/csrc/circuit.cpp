@@ -265,6 +265,20 @@ Circuit Builder::finalize() {
         c.sha_flat.insert(c.sha_flat.end(), blk.desc.begin(), blk.desc.end());
     }
 
+    c.regex_flat.clear();
+    c.regex_flat.push_back((uint32_t)c.regex_seeds.size());
+    for (auto& R : c.regex_seeds) {
+        c.regex_flat.insert(c.regex_flat.end(), {(uint32_t)(R.desc.size() / 2), (uint32_t)R.bytes.size(), R.n_states,
+                                                 (uint32_t)R.first_mask, (uint32_t)(R.first_mask >> 32)});
+        c.regex_flat.insert(c.regex_flat.end(), R.bytes.begin(), R.bytes.end());
+        for (uint32_t q = 0; q < R.n_states * 64; ++q) {
+            uint32_t wd = 0;
+            for (int k = 0; k < 4; ++k) wd |= (uint32_t)R.table[4 * (size_t)q + k] << (8 * k);
+            c.regex_flat.push_back(wd);
+        }
+        c.regex_flat.insert(c.regex_flat.end(), R.desc.begin(), R.desc.end());
+    }
+
     // Fuse "scratch <- LC; bits <- (scratch >> k) & mask" into OP_SHRLC when the scratch slot feeds nothing else:
     // the shift ops then sit one dependency level earlier (13.9 k -> 10.8 k levels for the default EmailVerifier).
     // ZKE_FUSED_SHRAND=0 keeps the two-op form (GPU witness == oracle verified in both forms).

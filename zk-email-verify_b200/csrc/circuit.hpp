@@ -92,6 +92,20 @@ enum ShaQuantity : uint32_t {
     SHA_Q_GROUPS = 17
 };
 
+// One zk-regex instance in the zk-regex circuit shape (regex.cpp: regex_circuit): the state signals of position i only
+// depend on the byte at i and the state signals of position i - 1 - a dependency chain as long as the message.  The set
+// of live DFA states per position is a plain automaton run, so a device can produce every state SIGNAL of the instance at
+// once ("seed" them) and the per-position gadgets (comparators, ANDs, ORs) of all positions then evaluate side by side.
+// The witness program keeps all of its ops - the seeded signals are simply written twice with the same value, and the
+// CPU oracle walks the program as it is (engine.cu: do_open uses the record when it levelises the program).
+struct RegexSeed {
+    uint32_t n_states = 0;            // <= 64
+    std::vector<uint32_t> bytes;      // the variable holding message byte j (position j + 1 of the circuit; position 0 is the marker)
+    std::vector<uint8_t> table;       // n_states x 256: destination of (source state, byte) or 0xff; byte 255 never fires
+    uint64_t first_mask = 1;          // live states after the marker position (bit 0 = state 0, always live)
+    std::vector<uint32_t> desc;       // 2 words per seeded signal: {variable, position << 8 | state}, position >= 1
+};
+
 struct SignalGroup {
     std::string name;
     uint32_t first;  // first witness index
@@ -128,6 +142,11 @@ struct Circuit {
     // flat image of sha_blocks: {n_blocks, then per block: var_begin, var_end, temp_begin, temp_end, n_desc, inputs[768],
     // desc[2 n_desc]} (built by finalize; ZKE_ARR_SHA_BLOCKS)
     std::vector<uint32_t> sha_flat;
+
+    std::vector<RegexSeed> regex_seeds; // zk-regex instances whose state signals can be produced by an automaton run (may be empty)
+    // flat image of regex_seeds: {n_seeds, then per seed: n_desc, n_bytes, n_states, first_mask lo, hi, bytes[n_bytes],
+    // table[n_states * 64] (4 bytes per word, little-endian), desc[2 n_desc]} (built by finalize; ZKE_ARR_REGEX_SEEDS)
+    std::vector<uint32_t> regex_flat;
 
     uint32_t n_levels() const { return level_ptr.empty() ? 0 : (uint32_t)level_ptr.size() - 1; }
     const SignalGroup* find_group(const std::string& n) const;
@@ -177,6 +196,7 @@ class Builder {
     uint32_t num_vars() const { return next_var_; }
     uint32_t num_temps() const { return next_temp_; }
     void add_sha_block(ShaBlock&& blk) { c_.sha_blocks.push_back(std::move(blk)); }   // temp range as raw temp indices
+    void add_regex_seed(RegexSeed&& sd) { c_.regex_seeds.push_back(std::move(sd)); }
     uint32_t num_constraints() const { return (uint32_t)c_.scope_of_constraint.size(); }
 
    private:

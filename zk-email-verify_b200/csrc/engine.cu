@@ -638,18 +638,44 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         // the program is levelised again - the chained compressions then cost one level each instead of ~320.
         bool native_sha = !c.sha_blocks.empty();
         if (const char* e = getenv("ZKE_NATIVE_SHA")) native_sha = native_sha && atoi(e) != 0;
-        static const uint32_t XOP_SHA = 6;
-        std::vector<WOp> xops;                         // code XOP_SHA: a = index of the block
+        // ---- zk-regex state seeding (circuit.hpp: RegexSeed; ZKE_NATIVE_REGEX=0 turns it off): one cooperative op per regex
+        // instance runs the automaton over the message and writes every state signal; the instance's own ops stay (they
+        // write the same values again) but now depend on seeded signals instead of on the previous position's gadgets, so the
+        // ~4 levels per message byte collapse into a handful for the whole message.
+        bool native_rx = !c.regex_seeds.empty();
+        if (const char* e = getenv("ZKE_NATIVE_REGEX")) native_rx = native_rx && atoi(e) != 0;
+        static const uint32_t XOP_SHA = 6, XOP_RX = 7;
+        std::vector<WOp> xops;                         // code XOP_SHA: a = index of the block; XOP_RX: a = index of the seed
         std::vector<uint32_t> xlevel_ptr;              // ops of level l: [xlevel_ptr[l], xlevel_ptr[l + 1])
         std::vector<uint32_t> aux = c.aux;
-        std::vector<uint32_t> sha_aux_off(c.sha_blocks.size(), 0);
-        if (!native_sha) {
+        std::vector<uint32_t> sha_aux_off(c.sha_blocks.size(), 0), rx_aux_off(c.regex_seeds.size(), 0);
+        if (!native_sha && !native_rx) {
             xops = c.ops;
             xlevel_ptr = c.level_ptr;
         } else {
             const uint32_t total = c.n_vars + c.n_temps;
             std::vector<int32_t> owner(total, -1);     // slot -> block that defines it
-            for (size_t bi = 0; bi < c.sha_blocks.size(); ++bi) {
+            std::vector<uint8_t> seeded(total, 0);     // slot written by a regex seed op (its own op stays)
+            if (native_rx)
+                for (size_t ri = 0; ri < c.regex_seeds.size(); ++ri) {
+                    const RegexSeed& R = c.regex_seeds[ri];
+                    rx_aux_off[ri] = (uint32_t)aux.size();
+                    aux.push_back((uint32_t)(R.desc.size() / 2));
+                    aux.push_back((uint32_t)R.bytes.size());
+                    aux.push_back(R.n_states);
+                    aux.push_back((uint32_t)R.first_mask);
+                    aux.push_back((uint32_t)(R.first_mask >> 32));
+                    aux.insert(aux.end(), R.bytes.begin(), R.bytes.end());
+                    for (uint32_t q = 0; q < R.n_states * 64; ++q) {
+                        uint32_t wd = 0;
+                        for (int k = 0; k < 4; ++k) wd |= (uint32_t)R.table[4 * (size_t)q + k] << (8 * k);
+                        aux.push_back(wd);
+                    }
+                    aux.insert(aux.end(), R.desc.begin(), R.desc.end());
+                    for (size_t d = 0; d < R.desc.size(); d += 2) seeded[R.desc[d]] = 1;
+                }
+            if (aux.size() >= (1u << 30)) throw std::runtime_error("witness program: auxiliary table too large");
+            for (size_t bi = 0; native_sha && bi < c.sha_blocks.size(); ++bi) {
                 const ShaBlock& B = c.sha_blocks[bi];
                 for (uint32_t v = B.var_begin; v < B.var_end; ++v) owner[v] = (int32_t)bi;
                 for (uint32_t v = B.temp_begin; v < B.temp_end; ++v) owner[v] = (int32_t)bi;
@@ -667,16 +693,22 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                 const uint32_t nd = o.code == OP_FPMUL ? 2 * c.aux[o.a + 1] : 1;
                 for (uint32_t j = 0; j < nd; ++j) def_pos[o.dst + j] = (int64_t)i;
             }
-            std::vector<std::vector<uint32_t>> blocks_at(c.ops.size() + 1);
-            for (size_t bi = 0; bi < c.sha_blocks.size(); ++bi) {
+            std::vector<std::vector<uint32_t>> blocks_at(c.ops.size() + 1), seeds_at(c.ops.size() + 1);
+            for (size_t bi = 0; native_sha && bi < c.sha_blocks.size(); ++bi) {
                 int64_t pos = 0;
                 for (uint32_t v : c.sha_blocks[bi].inputs) if (v < SHA_CONST0) pos = std::max(pos, def_pos[v] + 1);
                 blocks_at[(size_t)pos].push_back((uint32_t)bi);
+            }
+            for (size_t ri = 0; native_rx && ri < c.regex_seeds.size(); ++ri) {
+                int64_t pos = 0;      // right after the producer of the last message byte: before every op of the instance
+                for (uint32_t v : c.regex_seeds[ri].bytes) pos = std::max(pos, def_pos[v] + 1);
+                seeds_at[(size_t)pos].push_back((uint32_t)ri);
             }
             std::vector<WOp> kept;
             kept.reserve(c.ops.size());
             for (size_t i = 0; i <= c.ops.size(); ++i) {
                 for (uint32_t bi : blocks_at[i]) kept.push_back(WOp{XOP_SHA, c.sha_blocks[bi].var_begin, bi, 0, 0});
+                for (uint32_t ri : seeds_at[i]) kept.push_back(WOp{XOP_RX, 0, ri, 0, 0});
                 if (i < c.ops.size() && owner[c.ops[i].dst] < 0) kept.push_back(c.ops[i]);
             }
             // levelise (the same rules as Builder::finalize, plus the multi-output block op)
@@ -699,15 +731,23 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                     case OP_SHRAND: case OP_INVZ: l = need(o.a); break;
                     case OP_FPMUL: { const uint32_t kk = c.aux[o.a + 1]; for (uint32_t j = 0; j < 3 * kk; ++j) l = std::max(l, need(c.aux[o.a + 2 + j])); break; }
                     case XOP_SHA: for (uint32_t v : c.sha_blocks[o.a].inputs) if (v < SHA_CONST0) l = std::max(l, need(v)); break;
+                    case XOP_RX: for (uint32_t v : c.regex_seeds[o.a].bytes) l = std::max(l, need(v)); break;
                     default: throw std::runtime_error("bad opcode");
                 }
                 l += 1;
                 if (o.code == XOP_SHA) {
                     const ShaBlock& B = c.sha_blocks[o.a];
                     for (uint32_t v = B.var_begin; v < B.var_end; ++v) { defined[v] = 1; level[v] = l; }
+                } else if (o.code == XOP_RX) {
+                    const RegexSeed& R = c.regex_seeds[o.a];
+                    for (size_t d = 0; d < R.desc.size(); d += 2) { defined[R.desc[d]] = 1; level[R.desc[d]] = l; }
                 } else if (o.code == OP_FPMUL) {
                     const uint32_t kk = c.aux[o.a + 1];
                     for (uint32_t j = 0; j < 2 * kk; ++j) { defined[o.dst + j] = 1; level[o.dst + j] = l; }
+                } else if (seeded[o.dst]) {
+                    // the value is already there (same value, written by the seed op at an earlier level): readers keep
+                    // depending on the seed, this op only has to run after its own operands
+                    if (!defined[o.dst]) throw std::runtime_error("regex seeding: a seeded signal is produced before its seed op");
                 } else {
                     defined[o.dst] = 1; level[o.dst] = l;
                 }
@@ -736,6 +776,7 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
             const uint32_t coop_first = (uint32_t)(coop.size() / 2);
             for (uint32_t i = beg; i < end; ++i) {
                 if (xops[i].code == XOP_SHA) { coop.push_back(sha_aux_off[xops[i].a]); coop.push_back(0); }
+                else if (xops[i].code == XOP_RX) { coop.push_back(0x40000000u | rx_aux_off[xops[i].a]); coop.push_back(0); }
                 else if (xops[i].code == OP_FPMUL && coop_fpmul) { coop.push_back(0x80000000u | xops[i].a); coop.push_back(xops[i].dst); }
                 else order.push_back(i);
             }

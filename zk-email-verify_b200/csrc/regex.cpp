@@ -288,6 +288,22 @@ static LCVec regex_circuit(Builder& b, const Dfa& dfa, const LCVec& msg) {
     states[0] = one;
     LCVec accept_flags;
     LCVec out(1 + msg.size());
+    // record for the device's automaton run (circuit.hpp: RegexSeed): possible when every message byte is a plain signal
+    RegexSeed seed;
+    bool seedable = S <= 64 && msg.size() < (1u << 24);
+    for (size_t j = 0; j < msg.size() && seedable; ++j) {
+        Var v;
+        if (msg[j].is_single_var(&v)) seed.bytes.push_back(v); else seedable = false;
+    }
+    if (seedable) {
+        seed.n_states = (uint32_t)S;
+        seed.table.assign((size_t)S * 256, 0xff);
+        for (size_t k = 0; k < dfa.trans.size(); ++k) {
+            const DfaTransition& t = dfa.trans[k];
+            for (int c = 0; c < 255; ++c) if (t.cs.test(c)) seed.table[(size_t)t.src * 256 + c] = (uint8_t)t.dst;
+            if (t.src == 0 && t.cs.test(255)) seed.first_mask |= 1ull << t.dst;      // the marker byte: only state 0 is live before it
+        }
+    }
     for (size_t i = 0; i < num_bytes; ++i) {
         const bool is_marker = (i == 0);
         const LC in = is_marker ? LC::constant(Fr::from_u64(255)) : msg[i - 1];
@@ -325,10 +341,16 @@ static LCVec regex_circuit(Builder& b, const Dfa& dfa, const LCVec& msg) {
             out[i] = pubs.empty() ? LC() : b.mul(in, multi_or(b, pubs));   // reveal0[i-1] <== in[i] * is_reveal
         }
         states.swap(next);
+        if (seedable && !is_marker)
+            for (int s = 1; s < S; ++s) {
+                Var v;
+                if (states[s].is_single_var(&v)) { seed.desc.push_back(v); seed.desc.push_back(((uint32_t)i << 8) | (uint32_t)s); }
+            }
         for (int s = 1; s < S; ++s) if (dfa.accept[s] && !states[s].is_zero()) accept_flags.push_back(states[s]);
     }
     if (accept_flags.empty()) throw std::runtime_error("regex: accept state unreachable for this length");
     out[0] = multi_or(b, accept_flags);
+    if (seedable && !seed.desc.empty()) b.add_regex_seed(std::move(seed));
     return out;
 }
 

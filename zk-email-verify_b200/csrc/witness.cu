@@ -185,6 +185,62 @@ __device__ void sha_coop(const DevProgram& P, uint8_t* w, uint32_t aux_off, unsi
     __syncthreads();
 }
 
+// ---- zk-regex state seeding (circuit.hpp: RegexSeed) -------------------------------------------------------------------
+// The state signals of a zk-regex instance form a chain as long as the message (position i needs position i - 1); the
+// set of live DFA states per position is just an automaton run.  The CTA gathers the message bytes, one thread runs the
+// automaton (the live set is a 64-bit mask; state 0 is always live, byte 255 - the marker - fires nothing), and all
+// threads write the state signals of every position.  The instance's own ops follow at a handful of levels and write
+// the same values again; the CPU oracle walks only those, so "GPU witness == oracle witness" checks the seeding.
+// Shared buffer Q (SHA_Q_WORDS 64-bit words): masks of up to RX_CHUNK positions, then the staged bytes, carry at the end.
+static const uint32_t RX_CHUNK = 896;
+__device__ void regex_coop(const DevProgram& P, uint8_t* w, uint32_t aux_off, unsigned long long* Q) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t* ax = P.aux + aux_off;
+    const uint32_t n_desc = ax[0], n_bytes = ax[1], n_states = ax[2];
+    const unsigned long long first = (unsigned long long)ax[3] | ((unsigned long long)ax[4] << 32);
+    const uint32_t* bytes = ax + 5;
+    const uint8_t* table = reinterpret_cast<const uint8_t*>(bytes + n_bytes);
+    const uint32_t* desc = bytes + n_bytes + n_states * 64;
+    uint8_t* staged = reinterpret_cast<uint8_t*>(Q + RX_CHUNK);
+    for (uint32_t base = 0; base < n_bytes; base += RX_CHUNK) {
+        const uint32_t cnt = min(RX_CHUNK, n_bytes - base);
+        __syncthreads();                                           // the previous chunk's masks have been consumed
+        for (uint32_t j = tid; j < cnt; j += WITNESS_THREADS) {
+            const Fr v = Fr::load(w + 32ull * bytes[base + j]);
+            const bool is_byte = (v.v[1] | v.v[2] | v.v[3] | v.v[4] | v.v[5] | v.v[6] | v.v[7]) == 0 && v.v[0] < 255u;
+            staged[j] = is_byte ? (uint8_t)v.v[0] : (uint8_t)255;  // anything else fires no transition (and fails its range checks)
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned long long mask = base == 0 ? first : Q[SHA_Q_WORDS - 1];
+            for (uint32_t j = 0; j < cnt; ++j) {
+                const uint32_t c = staged[j];
+                unsigned long long next = 1ull, m = mask;
+                while (m) {
+                    const int st = __ffsll((long long)m) - 1;
+                    m &= m - 1;
+                    const uint32_t d = table[(uint32_t)st * 256u + c];
+                    if (d != 0xffu) next |= 1ull << d;
+                }
+                mask = next;
+                Q[j] = mask;
+            }
+            Q[SHA_Q_WORDS - 1] = mask;
+        }
+        __syncthreads();
+        for (uint32_t dd = tid; dd < n_desc; dd += WITNESS_THREADS) {
+            const uint32_t var = desc[2 * dd], ps = desc[2 * dd + 1];
+            const uint32_t j = (ps >> 8) - 1u - base;              // position p reads message byte p - 1
+            if (j < cnt) {
+                Fr o = Fr::zero();
+                o.v[0] = (uint32_t)((Q[j] >> (ps & 255u)) & 1ull);
+                o.store(w + 32ull * var);
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // ---- cooperative FpMul hint ---------------------------------------------------------------------------------------
 // (q, r) = divmod(A * B, P) on 2048-bit integers.  The sequential Knuth division above costs ~0.66 ms per call in one
 // thread and the 17 chained calls of RSAVerifier65537 were a third of the witness kernel after the SHA substitution.
@@ -413,6 +469,7 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
         for (uint32_t q = 0; q < hdr.w; ++q) {
             const uint32_t c0 = P.coop[2 * (hdr.z + q)], c1 = P.coop[2 * (hdr.z + q) + 1];
             if (c0 >> 31) fpmul_coop(P, w, c0 & 0x7fffffffu, c1, fpmul_s);
+            else if (c0 & 0x40000000u) regex_coop(P, w, c0 & 0x3fffffffu, sha_q);
             else sha_coop(P, w, c0, sha_q, sha_in);
         }
         cp_async_wait_all();

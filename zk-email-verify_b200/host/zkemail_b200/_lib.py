@@ -52,6 +52,7 @@ zke_version = _sig("zke_version", c_char_p, [])
 (ARR_COEFS, ARR_A_PTR, ARR_A_VAR, ARR_A_COEF, ARR_B_PTR, ARR_B_VAR, ARR_B_COEF, ARR_C_PTR, ARR_C_VAR, ARR_C_COEF,
  ARR_OPS, ARR_LEVEL_PTR, ARR_LC_PTR, ARR_LC_VAR, ARR_LC_COEF, ARR_AUX, ARR_SCOPE_OF_CONSTRAINT) = range(17)
 ARR_SHA_BLOCKS = 17
+ARR_REGEX_SEEDS = 18
 
 
 class ZkeError(RuntimeError):
