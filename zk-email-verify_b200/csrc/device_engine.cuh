@@ -27,7 +27,8 @@ extern unsigned long long g_kernel_launches;
 static const uint32_t WOP_NOP = 15;
 struct DevProgram {
     const uint4* ops;            // [n_iters][WITNESS_THREADS]
-    const uint4* iter_hdr;       // [n_iters + 2]: {first term (even), term count (even), first cooperative op, their count}
+    const uint4* iter_hdr;       // [n_iters + 2 * cluster]: {first term (even), term count (even), first cooperative op, their count
+                                 // | 1 << 31 on the iterations of a level's last round (cluster > 1: barrier across the CTAs)}
     const uint32_t* coop;        // cooperative ops of the iterations (executed by the whole CTA), two words each:
                                  // {offset into `aux`, 0}: native Sha256compression table ({n_desc, inputs[768],
                                  // desc[n_desc][2]}, circuit.hpp: ShaBlock); {1 << 31 | offset into `aux`, dst}: FpMul hint
@@ -37,6 +38,8 @@ struct DevProgram {
     const uint8_t* small_inv;    // [n_small_inv][32]: x^-1 mod r in standard form, entry 0 unused
     uint32_t n_small_inv;
     uint32_t n_iters, n_ops, n_vars, n_temps, n_outputs, n_inputs;
+    uint32_t cluster;            // CTAs per email (thread-block cluster): iteration k belongs to CTA k % cluster, every level is
+                                 // padded to whole rounds of `cluster` iterations (1: one CTA walks all of them)
     unsigned long long* trace;   // optional (diagnostics): clock64() of CTA 0 after every iteration
 };
 

@@ -770,8 +770,16 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         if (const char* e = getenv("ZKE_COOP_FPMUL")) coop_fpmul = atoi(e) != 0;
         std::vector<uint32_t> order;
         std::vector<uint64_t> keys;
+        // ZKE_WITNESS_CLUSTER = 2 / 4 / 8: thread-block cluster of that many CTAs per email (witness.cu); every level is padded to
+        // whole rounds of `cluster` iterations, iteration k belongs to CTA k % cluster
+        // (default: as many CTAs per email as still fit one wave of the GPU's SMs at this context's batch size - a witness
+        // CTA owns an SM; ZKE_WITNESS_CLUSTER=1 keeps one CTA per email).  Measured on B200, default circuit: batch 64,
+        // 2 CTAs per email 10.0 ms against 12.6 ms per batch; one email, 8 CTAs: fullProve 33.4 ms against 38.5 ms.
+        uint32_t cluster = max_batch <= 8 ? 8 : (max_batch <= 32 ? 4 : (max_batch <= 74 ? 2 : 1));
+        if (const char* e = getenv("ZKE_WITNESS_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) cluster = (uint32_t)v; }
         for (uint32_t lvl = 0; lvl < n_xlevels; ++lvl) {
             const uint32_t beg = xlevel_ptr[lvl], end = xlevel_ptr[lvl + 1];
+            const size_t level_first_iter = hdr.size() / 4;
             order.clear();
             const uint32_t coop_first = (uint32_t)(coop.size() / 2);
             for (uint32_t i = beg; i < end; ++i) {
@@ -850,9 +858,16 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                 x->iter_info.push_back((uint32_t)std::min<size_t>(T, n_regular > base ? n_regular - base : 0));
                 x->iter_info.push_back((uint32_t)(terms.size() / 2) - first_term);
             }
+            // pad the level to whole rounds (empty iterations: no-op records, no terms) and flag its last round
+            while (cluster > 1 && (hdr.size() / 4 - level_first_iter) % cluster != 0) {
+                for (uint32_t t = 0; t < T; ++t) { const uint32_t rec[4] = {0, dev::WOP_NOP, 0, 0}; packed.insert(packed.end(), rec, rec + 4); }
+                hdr.push_back((uint32_t)(terms.size() / 2)); hdr.push_back(0); hdr.push_back((uint32_t)(coop.size() / 2)); hdr.push_back(0);
+                x->iter_info.push_back(dev::WOP_NOP); x->iter_info.push_back(0); x->iter_info.push_back(0);
+            }
+            for (uint32_t q = 1; q <= cluster && hdr.size() / 4 >= level_first_iter + q; ++q) hdr[hdr.size() - 4 * q + 3] |= 0x80000000u;
         }
         const uint32_t n_iters = (uint32_t)(hdr.size() / 4);
-        for (int q = 0; q < 2; ++q) { hdr.push_back((uint32_t)(terms.size() / 2)); hdr.push_back(0); hdr.push_back(0); hdr.push_back(0); }   // two sentinel headers
+        for (uint32_t q = 0; q < 2 * cluster; ++q) { hdr.push_back((uint32_t)(terms.size() / 2)); hdr.push_back(0); hdr.push_back(0); hdr.push_back(0); }   // sentinel headers
         if (packed.empty()) packed.resize(4 * T, 0);
         for (int q = 0; q < 8; ++q) terms.push_back(0);
         x->ops.upload(packed);
@@ -874,6 +889,7 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         P.terms = (const uint2*)x->lc_terms.p; P.aux = (const uint32_t*)x->aux.p; P.coef_r = x->coef_r.p;
         P.small_inv = x->small_inv.p; P.n_small_inv = NSMALL;
         P.trace = nullptr;
+        P.cluster = cluster;
         P.n_iters = n_iters; P.n_ops = (uint32_t)c.ops.size(); P.n_vars = c.n_vars; P.n_temps = c.n_temps;
         P.n_outputs = c.n_outputs; P.n_inputs = c.n_inputs();
     }

@@ -403,8 +403,14 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
     __shared__ uint32_t sha_in[24];
     __shared__ FpmulShared fpmul_s;
     if (threadIdx.x == 0) fpmul_s.t_cached = -1;        // no reciprocal cached yet (ordered by the first barrier below)
-    const uint32_t email = blockIdx.x;
-    if (email >= batch) return;
+    // thread-block cluster of P.cluster CTAs per email: the iterations of a level are dealt round-robin to the CTAs
+    // (iteration k -> CTA k % cluster; the host pads every level to whole rounds), a cluster barrier with release /
+    // acquire semantics ends each level.  cluster == 1 is the plain one-CTA-per-email kernel.
+    const uint32_t CL = P.cluster ? P.cluster : 1;
+    uint32_t rank = 0;
+    if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const uint32_t email = blockIdx.x / CL;
+    if (email >= batch) return;                          // (whole clusters: every CTA of a cluster shares `email`)
     uint8_t* w = w_all + 32ull * stride_elems * email;
     const uint32_t tid = threadIdx.x;
 
@@ -423,23 +429,23 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
 
     // software pipeline: op records one iteration ahead (registers), term blocks one iteration ahead (cp.async into
     // the other shared-memory buffer), iteration headers two ahead
-    uint4 hdr = P.iter_hdr[0], hdr_next = P.iter_hdr[1];
-    uint4 op = P.ops[tid];
+    uint4 hdr = P.iter_hdr[rank], hdr_next = P.iter_hdr[rank + CL];
+    uint4 op = P.ops[(size_t)rank * WITNESS_THREADS + tid];
     stage_terms(P, term_buf, hdr);
     cp_async_wait_all();
     __syncthreads();
 
-    for (uint32_t k = 0; k < P.n_iters; ++k) {
-        const uint4 hdr_next2 = P.iter_hdr[k + 2];      // the table has two sentinel entries
+    for (uint32_t k = rank, it = 0; k < P.n_iters; k += CL, ++it) {
+        const uint4 hdr_next2 = P.iter_hdr[k + 2 * CL];      // the table has 2 * cluster sentinel entries
         uint4 op_next = make_uint4(0, WOP_NOP, 0, 0);
-        if (k + 1 < P.n_iters) {
-            op_next = P.ops[(size_t)(k + 1) * WITNESS_THREADS + tid];
-            stage_terms(P, term_buf + ((k + 1) & 1) * WITNESS_TERM_BUF, hdr_next);
+        if (k + CL < P.n_iters) {
+            op_next = P.ops[(size_t)(k + CL) * WITNESS_THREADS + tid];
+            stage_terms(P, term_buf + ((it + 1) & 1) * WITNESS_TERM_BUF, hdr_next);
         }
         const uint32_t code = op.y & 0xffu;
         if (code <= 1 || code == 5) {   // OP_LIN: dst = A ; OP_QUAD: dst = A*B + C ; OP_SHRLC: dst = (A >> shift) & mask
             const uint32_t nA = (op.y >> 8) & 31u, nB = (op.y >> 13) & 31u, nC = (op.y >> 18) & 31u;
-            const uint2* t = hdr.y > WITNESS_TERM_BUF ? P.terms + op.z : term_buf + (k & 1) * WITNESS_TERM_BUF + (op.z - hdr.x);
+            const uint2* t = hdr.y > WITNESS_TERM_BUF ? P.terms + op.z : term_buf + (it & 1) * WITNESS_TERM_BUF + (op.z - hdr.x);
             Fr xa, xb, xc;
             eval_lcs(P, w, t, nA, nB, nC, xa, xb, xc);
             if (code == 1) {
@@ -466,7 +472,7 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
         }
         // cooperative ops of this iteration (native Sha256compression): the whole CTA works on each in turn; they only
         // read signals of earlier levels and define signals nothing else in this iteration touches
-        for (uint32_t q = 0; q < hdr.w; ++q) {
+        for (uint32_t q = 0; q < (hdr.w & 0xffffu); ++q) {
             const uint32_t c0 = P.coop[2 * (hdr.z + q)], c1 = P.coop[2 * (hdr.z + q) + 1];
             if (c0 >> 31) fpmul_coop(P, w, c0 & 0x7fffffffu, c1, fpmul_s);
             else if (c0 & 0x40000000u) regex_coop(P, w, c0 & 0x3fffffffu, sha_q);
@@ -474,6 +480,8 @@ witness_kernel(DevProgram P, uint8_t* __restrict__ w_all, size_t stride_elems, c
         }
         cp_async_wait_all();
         __syncthreads();     // level barrier and hand-over of the staged term block
+        if (CL > 1 && (hdr.w >> 31))      // last round of a level: the other CTAs' signals become visible here
+            asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
         if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[k] = clock64();
         op = op_next; hdr = hdr_next; hdr_next = hdr_next2;
     }
@@ -491,7 +499,21 @@ cudaError_t configure_witness_kernel() {
 
 void launch_witness(const DevProgram& P, uint8_t* w_all, size_t stride_elems, const uint8_t* inputs, uint32_t batch, cudaStream_t st) {
     static const bool slim = getenv("ZKE_WITNESS_SLIM") && atoi(getenv("ZKE_WITNESS_SLIM")) != 0;
-    if (slim) witness_kernel<2><<<batch, WITNESS_THREADS, WITNESS_SMEM, st>>>(P, w_all, stride_elems, inputs, batch);
+    if (P.cluster > 1) {
+        // one thread-block cluster per email (P.cluster CTAs on neighbouring SMs; the program stream was cut for it)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(batch * P.cluster, 1, 1);
+        cfg.blockDim = dim3(WITNESS_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = WITNESS_SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = P.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, witness_kernel<1>, P, w_all, stride_elems, inputs, batch);
+    }
+    else if (slim) witness_kernel<2><<<batch, WITNESS_THREADS, WITNESS_SMEM, st>>>(P, w_all, stride_elems, inputs, batch);
     else witness_kernel<1><<<batch, WITNESS_THREADS, WITNESS_SMEM, st>>>(P, w_all, stride_elems, inputs, batch);
     ZKE_COUNT_LAUNCH(1);
 }
