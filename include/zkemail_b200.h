@@ -88,10 +88,11 @@ enum {
     ZKE_ARR_SHA_BLOCKS = 17, /* uint32: {n_blocks, per block: var_begin, var_end, temp_begin, temp_end, n_desc,
                                inputs[768], desc[n_desc][2] = {signal, quantity << 8 | bit}} - the Sha256compression
                                instances the engine evaluates natively (one compression instead of ~320 levels)  */
-    ZKE_ARR_REGEX_SEEDS = 18 /* uint32: {n_seeds, per seed: n_desc, n_bytes, n_states, first_mask lo, hi, bytes[n_bytes]
-                               (signal of message byte j), table[n_states * 64] (destination state of (source, byte),
-                               0xff = none, 4 per word), desc[n_desc][2] = {signal, position << 8 | state}} - the zk-regex
-                               instances whose state signals the engine seeds with one automaton run               */
+    ZKE_ARR_REGEX_SEEDS = 18 /* uint32: {n_seeds, per seed: n_desc, n_bytes, n_states | mode << 31, first_mask lo, hi,
+                               bytes[n_bytes] (signal of message byte j), table[n_states * 64] (destination state of
+                               (source, byte), 0xff = none, 4 per word), mode 1 (compact shape): group[n_states * 64] (the
+                               product that fires), desc[n_desc][2] = {signal, position << 8 | state or product}} - the
+                               regex instances whose chained signals the engine seeds with one automaton run      */
 };
 const void* zke_circuit_array(const zke_circuit* c, int which, size_t* n_elems);
 const char* zke_circuit_scope_name(const zke_circuit* c, uint32_t scope_index);

@@ -37,7 +37,8 @@ def analyse(c, native_sha=True, native_rx=True):
     seeds, pos = [], 1
     for _ in range(int(rx[0]) if len(rx) and native_rx else 0):
         nd, nb, ns = (int(x) for x in rx[pos:pos + 3]); pos += 5
-        byts = [int(v) for v in rx[pos:pos + nb]]; pos += nb + 64 * ns
+        mode, ns = ns >> 31, ns & 0x7fffffff
+        byts = [int(v) for v in rx[pos:pos + nb]]; pos += nb + 64 * ns * (1 + mode)
         seeds.append((byts, [int(v) for v in rx[pos:pos + 2 * nd:2]])); pos += 2 * nd
     seeded = np.zeros(n_slots + 1, dtype=bool)
     for _, vs in seeds:

@@ -19,18 +19,31 @@ def _seeds(circuit):
     out, pos = [], 1
     for _ in range(flat[0]):
         nd, nb, ns, lo, hi = flat[pos:pos + 5]; pos += 5
+        mode, ns = ns >> 31, ns & 0x7fffffff
         bytes_ = flat[pos:pos + nb]; pos += nb
-        words = flat[pos:pos + 64 * ns]; pos += 64 * ns
-        table = [(wd >> (8 * k)) & 0xff for wd in words for k in range(4)]
+        unpack = lambda words: [(wd >> (8 * k)) & 0xff for wd in words for k in range(4)]
+        table = unpack(flat[pos:pos + 64 * ns]); pos += 64 * ns
+        group = None
+        if mode == 1:
+            group = unpack(flat[pos:pos + 64 * ns]); pos += 64 * ns
         desc = flat[pos:pos + 2 * nd]; pos += 2 * nd
-        out.append({"n_states": ns, "first": lo | (hi << 32), "bytes": bytes_, "table": table, "desc": desc})
+        out.append({"mode": mode, "n_states": ns, "first": lo | (hi << 32), "bytes": bytes_, "table": table, "group": group, "desc": desc})
     assert pos == len(flat)
     return out
 
 
 def _live_sets(seed, msg):
-    """masks[j] = live states after message byte j (position j + 1 of the circuit); the device op's loop."""
+    """masks[j] = live states after message byte j (position j + 1 of the circuit); the device op's loop.
+    Compact shape (mode 1): one state per position, masks[j] = 1 << (product that fires at byte j), 0 if none."""
     masks, mask = [], seed["first"]
+    if seed["mode"] == 1:
+        q = seed["first"]
+        for c in msg:
+            c = c if c < 255 else 255
+            g, d = seed["group"][256 * q + c], seed["table"][256 * q + c]
+            masks.append(0 if g == 0xff else 1 << g)
+            q = 0 if d == 0xff else d
+        return masks
     for c in msg:
         c = c if c < 255 else 255
         nxt = 1
@@ -56,7 +69,7 @@ def _check(circuit, inputs, msg_of_seed):
         assert len(desc) > 0 and all(seed["table"][256 * s + 255] == 0xff for s in range(seed["n_states"]))
         for k in range(0, len(desc), 2):
             var, pos, st = desc[k], desc[k + 1] >> 8, desc[k + 1] & 0xff
-            assert 1 <= pos <= len(msg) and 1 <= st < seed["n_states"]
+            assert 1 <= pos <= len(msg) and (seed["mode"] == 1 or 1 <= st < seed["n_states"])
             assert w[var] == (masks[pos - 1] >> st) & 1, (pos, st)
         total += len(desc) // 2
     return total
@@ -73,8 +86,18 @@ def test_body_hash_regex_seed_table():
         if any(b == 255 for b in padded):
             continue                                   # 255 is the marker byte: not a valid message byte for this circuit
         assert _check(c, {"msg": padded}, [padded]) > 1000
-    # the compact shape carries one one-hot state per position and records nothing
-    assert _seeds(z.Circuit("BodyHashRegex", [128, 1])) == []
+
+
+def test_compact_shape_seed_table():
+    """The compact shape carries ONE one-hot state per position; its chain runs through the `fire` products (mode 1)."""
+    c = z.Circuit("BodyHashRegex", [128, 1])
+    assert [sd["mode"] for sd in _seeds(c)] == [1]
+    hdr = b"to:a@b.c\r\ndkim-signature:v=1; a=rsa-sha256; bh=7xQMDuoVVU4m0W0WRVSrVXMeGSIASsnucK9dJsrc+vU=; h=from:to; b="
+    rng = random.Random(5)
+    alphabet = b"dkim-signature:bh=; \r\nazAZ09+/v\xc3\xa4\x00"
+    for msg in [hdr, b"", b"dkim-signature:v=1; d=x; bh=QUJD; b="] + [bytes(rng.choice(alphabet) for _ in range(rng.randrange(1, 128))) for _ in range(6)]:
+        padded = list(msg) + [0] * (128 - len(msg))
+        assert _check(c, {"msg": padded}, [padded]) > 1000
 
 
 def test_email_verifier_seed_table_on_a_signed_email():

@@ -243,6 +243,23 @@ bool Builder::default_fuse_shrand() {
     return e ? atoi(e) != 0 : true;
 }
 
+// flat image of one RegexSeed (circuit.hpp); also what the engine appends to the device program's aux table
+void append_regex_seed(std::vector<uint32_t>& out, const RegexSeed& R) {
+    out.insert(out.end(), {(uint32_t)(R.desc.size() / 2), (uint32_t)R.bytes.size(), R.n_states | (R.mode << 31),
+                           (uint32_t)R.first_mask, (uint32_t)(R.first_mask >> 32)});
+    out.insert(out.end(), R.bytes.begin(), R.bytes.end());
+    auto pack = [&](const std::vector<uint8_t>& t) {
+        for (uint32_t q = 0; q < R.n_states * 64; ++q) {
+            uint32_t wd = 0;
+            for (int k = 0; k < 4; ++k) wd |= (uint32_t)t[4 * (size_t)q + k] << (8 * k);
+            out.push_back(wd);
+        }
+    };
+    pack(R.table);
+    if (R.mode == 1) pack(R.group);
+    out.insert(out.end(), R.desc.begin(), R.desc.end());
+}
+
 Circuit Builder::finalize() {
     Circuit& c = c_;
     c.n_vars = next_var_;
@@ -268,15 +285,7 @@ Circuit Builder::finalize() {
     c.regex_flat.clear();
     c.regex_flat.push_back((uint32_t)c.regex_seeds.size());
     for (auto& R : c.regex_seeds) {
-        c.regex_flat.insert(c.regex_flat.end(), {(uint32_t)(R.desc.size() / 2), (uint32_t)R.bytes.size(), R.n_states,
-                                                 (uint32_t)R.first_mask, (uint32_t)(R.first_mask >> 32)});
-        c.regex_flat.insert(c.regex_flat.end(), R.bytes.begin(), R.bytes.end());
-        for (uint32_t q = 0; q < R.n_states * 64; ++q) {
-            uint32_t wd = 0;
-            for (int k = 0; k < 4; ++k) wd |= (uint32_t)R.table[4 * (size_t)q + k] << (8 * k);
-            c.regex_flat.push_back(wd);
-        }
-        c.regex_flat.insert(c.regex_flat.end(), R.desc.begin(), R.desc.end());
+        append_regex_seed(c.regex_flat, R);
     }
 
     // Fuse "scratch <- LC; bits <- (scratch >> k) & mask" into OP_SHRLC when the scratch slot feeds nothing else:

@@ -104,7 +104,15 @@ struct RegexSeed {
     std::vector<uint8_t> table;       // n_states x 256: destination of (source state, byte) or 0xff; byte 255 never fires
     uint64_t first_mask = 1;          // live states after the marker position (bit 0 = state 0, always live)
     std::vector<uint32_t> desc;       // 2 words per seeded signal: {variable, position << 8 | state}, position >= 1
+    // mode 1 - the compact shape (regex.cpp: regex_circuit_compact): ONE state per position (the automaton of live-state
+    // sets is deterministic, n_states <= 255, first_mask = the state after the marker), the chain runs through the `fire`
+    // products: `group` gives the product that fires on (state, byte) (0xff: none, the next state is then 0), and a
+    // descriptor {variable, position << 8 | product id} is 1 exactly when that product fires at that position.
+    uint32_t mode = 0;
+    std::vector<uint8_t> group;       // mode 1: n_states x 256
 };
+
+void append_regex_seed(std::vector<uint32_t>& out, const RegexSeed& R);   // flat image (circuit.cpp)
 
 struct SignalGroup {
     std::string name;
@@ -144,8 +152,9 @@ struct Circuit {
     std::vector<uint32_t> sha_flat;
 
     std::vector<RegexSeed> regex_seeds; // zk-regex instances whose state signals can be produced by an automaton run (may be empty)
-    // flat image of regex_seeds: {n_seeds, then per seed: n_desc, n_bytes, n_states, first_mask lo, hi, bytes[n_bytes],
-    // table[n_states * 64] (4 bytes per word, little-endian), desc[2 n_desc]} (built by finalize; ZKE_ARR_REGEX_SEEDS)
+    // flat image of regex_seeds: {n_seeds, then per seed: n_desc, n_bytes, n_states | mode << 31, first_mask lo, hi,
+    // bytes[n_bytes], table[n_states * 64] (4 bytes per word, little-endian), mode 1: group[n_states * 64], desc[2 n_desc]}
+    // (built by finalize; ZKE_ARR_REGEX_SEEDS); the engine appends the same image to the program's aux table
     std::vector<uint32_t> regex_flat;
 
     uint32_t n_levels() const { return level_ptr.empty() ? 0 : (uint32_t)level_ptr.size() - 1; }

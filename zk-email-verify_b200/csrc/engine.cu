@@ -660,18 +660,7 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                 for (size_t ri = 0; ri < c.regex_seeds.size(); ++ri) {
                     const RegexSeed& R = c.regex_seeds[ri];
                     rx_aux_off[ri] = (uint32_t)aux.size();
-                    aux.push_back((uint32_t)(R.desc.size() / 2));
-                    aux.push_back((uint32_t)R.bytes.size());
-                    aux.push_back(R.n_states);
-                    aux.push_back((uint32_t)R.first_mask);
-                    aux.push_back((uint32_t)(R.first_mask >> 32));
-                    aux.insert(aux.end(), R.bytes.begin(), R.bytes.end());
-                    for (uint32_t q = 0; q < R.n_states * 64; ++q) {
-                        uint32_t wd = 0;
-                        for (int k = 0; k < 4; ++k) wd |= (uint32_t)R.table[4 * (size_t)q + k] << (8 * k);
-                        aux.push_back(wd);
-                    }
-                    aux.insert(aux.end(), R.desc.begin(), R.desc.end());
+                    append_regex_seed(aux, R);
                     for (size_t d = 0; d < R.desc.size(); d += 2) seeded[R.desc[d]] = 1;
                 }
             if (aux.size() >= (1u << 30)) throw std::runtime_error("witness program: auxiliary table too large");

@@ -482,6 +482,26 @@ LCVec regex_circuit_compact(Builder& b, const Dfa& dfa, const LCVec& msg) {
     auto count_accepts = [&]() { for (int s = 0; s < S; ++s) if (pd.accept[s] && !states[s].is_zero()) accepted += states[s]; };
     count_accepts();
     LCVec out(1 + msg.size());
+    // record for the device's automaton run (circuit.hpp: RegexSeed, mode 1): the chain runs through the `fire` products
+    RegexSeed seed;
+    std::map<std::tuple<int, bool, std::string>, int> gid;           // (dst, public, class) -> product id, the same at every position
+    for (auto& t : pd.trans) gid.emplace(std::make_tuple(t.dst, t.pub, t.cs.to_string()), (int)gid.size());
+    bool seedable = S <= 255 && gid.size() <= 254 && msg.size() < (1u << 24);
+    for (size_t j = 0; j < msg.size() && seedable; ++j) {
+        Var v;
+        if (msg[j].is_single_var(&v)) seed.bytes.push_back(v); else seedable = false;
+    }
+    if (seedable) {
+        seed.mode = 1;
+        seed.n_states = (uint32_t)S;
+        seed.first_mask = (uint64_t)pd.after_marker;
+        seed.table.assign((size_t)S * 256, 0xff);
+        seed.group.assign((size_t)S * 256, 0xff);
+        for (auto& t : pd.trans) {
+            const int g = gid[std::make_tuple(t.dst, t.pub, t.cs.to_string())];
+            for (int c = 0; c < 256; ++c) if (t.cs.test(c)) { seed.table[(size_t)t.src * 256 + c] = (uint8_t)t.dst; seed.group[(size_t)t.src * 256 + c] = (uint8_t)g; }
+        }
+    }
     for (size_t i = 0; i < msg.size(); ++i) {
         const ByteOneHot oh = byte_one_hot(b, msg[i]);
         std::map<std::pair<uint32_t, uint32_t>, LC> cache;
@@ -505,6 +525,8 @@ LCVec regex_circuit_compact(Builder& b, const Dfa& dfa, const LCVec& msg) {
                 ScopeGuard g(b, "AND");
                 fire = src.is_const() ? m * src.const_value() : b.mul(src, m);
             }
+            Var fv;
+            if (seedable && fire.is_single_var(&fv)) { seed.desc.push_back(fv); seed.desc.push_back((uint32_t)((i + 1) << 8) | (uint32_t)gid[kv.first]); }
             next[std::get<0>(kv.first)] += fire;
             moved += fire;
             if (std::get<1>(kv.first)) reveal += fire;
@@ -516,6 +538,7 @@ LCVec regex_circuit_compact(Builder& b, const Dfa& dfa, const LCVec& msg) {
     }
     if (accepted.is_zero()) throw std::runtime_error("regex: accept state unreachable for this length");
     out[0] = b.signal(one - is_zero(b, accepted));
+    if (seedable && !seed.desc.empty()) b.add_regex_seed(std::move(seed));
     return out;
 }
 

@@ -196,11 +196,12 @@ static const uint32_t RX_CHUNK = 896;
 __device__ void regex_coop(const DevProgram& P, uint8_t* w, uint32_t aux_off, unsigned long long* Q) {
     const uint32_t tid = threadIdx.x;
     const uint32_t* ax = P.aux + aux_off;
-    const uint32_t n_desc = ax[0], n_bytes = ax[1], n_states = ax[2];
+    const uint32_t n_desc = ax[0], n_bytes = ax[1], n_states = ax[2] & 0x7fffffffu, mode = ax[2] >> 31;
     const unsigned long long first = (unsigned long long)ax[3] | ((unsigned long long)ax[4] << 32);
     const uint32_t* bytes = ax + 5;
     const uint8_t* table = reinterpret_cast<const uint8_t*>(bytes + n_bytes);
-    const uint32_t* desc = bytes + n_bytes + n_states * 64;
+    const uint8_t* group = table + n_states * 256u;                  // mode 1 only
+    const uint32_t* desc = bytes + n_bytes + n_states * 64 * (1 + mode);
     uint8_t* staged = reinterpret_cast<uint8_t*>(Q + RX_CHUNK);
     for (uint32_t base = 0; base < n_bytes; base += RX_CHUNK) {
         const uint32_t cnt = min(RX_CHUNK, n_bytes - base);
@@ -213,7 +214,13 @@ __device__ void regex_coop(const DevProgram& P, uint8_t* w, uint32_t aux_off, un
         __syncthreads();
         if (tid == 0) {
             unsigned long long mask = base == 0 ? first : Q[SHA_Q_WORDS - 1];
-            for (uint32_t j = 0; j < cnt; ++j) {
+            for (uint32_t j = 0; mode == 1 && j < cnt; ++j) {     // compact shape: one state, Q[j] = the product that fires
+                const uint32_t at = (uint32_t)mask * 256u + staged[j];
+                const uint32_t d = table[at];
+                Q[j] = group[at];
+                mask = d != 0xffu ? d : 0u;
+            }
+            for (uint32_t j = 0; mode == 0 && j < cnt; ++j) {
                 const uint32_t c = staged[j];
                 unsigned long long next = 1ull, m = mask;
                 while (m) {
@@ -233,7 +240,7 @@ __device__ void regex_coop(const DevProgram& P, uint8_t* w, uint32_t aux_off, un
             const uint32_t j = (ps >> 8) - 1u - base;              // position p reads message byte p - 1
             if (j < cnt) {
                 Fr o = Fr::zero();
-                o.v[0] = (uint32_t)((Q[j] >> (ps & 255u)) & 1ull);
+                o.v[0] = mode == 1 ? (uint32_t)(Q[j] == (ps & 255u)) : (uint32_t)((Q[j] >> (ps & 255u)) & 1ull);
                 o.store(w + 32ull * var);
             }
         }
