@@ -766,6 +766,7 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
         // 2 CTAs per email 10.0 ms against 12.6 ms per batch; one email, 8 CTAs: fullProve 33.4 ms against 38.5 ms.
         uint32_t cluster = max_batch <= 8 ? 8 : (max_batch <= 32 ? 4 : (max_batch <= 74 ? 2 : 1));
         if (const char* e = getenv("ZKE_WITNESS_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) cluster = (uint32_t)v; }
+        std::vector<std::pair<size_t, size_t>> level_iters;   // per level: index of its first iteration, number of non-empty ones
         for (uint32_t lvl = 0; lvl < n_xlevels; ++lvl) {
             const uint32_t beg = xlevel_ptr[lvl], end = xlevel_ptr[lvl + 1];
             const size_t level_first_iter = hdr.size() / 4;
@@ -847,15 +848,24 @@ static zke_ctx* do_open(const zke_circuit* zc, const zke_zkey* zk, int device, u
                 x->iter_info.push_back((uint32_t)std::min<size_t>(T, n_regular > base ? n_regular - base : 0));
                 x->iter_info.push_back((uint32_t)(terms.size() / 2) - first_term);
             }
-            // pad the level to whole rounds (empty iterations: no-op records, no terms) and flag its last round
+            // pad the level to whole rounds (empty iterations: no-op records, no terms)
+            level_iters.emplace_back(level_first_iter, hdr.size() / 4 - level_first_iter);
             while (cluster > 1 && (hdr.size() / 4 - level_first_iter) % cluster != 0) {
                 for (uint32_t t = 0; t < T; ++t) { const uint32_t rec[4] = {0, dev::WOP_NOP, 0, 0}; packed.insert(packed.end(), rec, rec + 4); }
                 hdr.push_back((uint32_t)(terms.size() / 2)); hdr.push_back(0); hdr.push_back((uint32_t)(coop.size() / 2)); hdr.push_back(0);
                 x->iter_info.push_back(dev::WOP_NOP); x->iter_info.push_back(0); x->iter_info.push_back(0);
             }
-            for (uint32_t q = 1; q <= cluster && hdr.size() / 4 >= level_first_iter + q; ++q) hdr[hdr.size() - 4 * q + 3] |= 0x80000000u;
         }
         const uint32_t n_iters = (uint32_t)(hdr.size() / 4);
+        // Cluster barrier flags (bit 31 of header word 3, on every iteration of a level's last round): needed when signals cross
+        // CTAs - the level had more than one iteration (other CTAs wrote) or the next one has (other CTAs will read).  Runs of
+        // one-iteration levels (the Poseidon rounds, the tails of the comparison chains) stay on CTA 0 with its own barrier.
+        for (size_t l = 0; l < level_iters.size(); ++l) {
+            const bool last = l + 1 == level_iters.size();
+            if (!(level_iters[l].second > 1 || last || level_iters[l + 1].second > 1)) continue;
+            const size_t end_iter = last ? n_iters : level_iters[l + 1].first;
+            for (uint32_t q = 1; q <= cluster && end_iter >= level_iters[l].first + q; ++q) hdr[4 * (end_iter - q) + 3] |= 0x80000000u;
+        }
         for (uint32_t q = 0; q < 2 * cluster; ++q) { hdr.push_back((uint32_t)(terms.size() / 2)); hdr.push_back(0); hdr.push_back(0); hdr.push_back(0); }   // sentinel headers
         if (packed.empty()) packed.resize(4 * T, 0);
         for (int q = 0; q < 8; ++q) terms.push_back(0);
