@@ -56,6 +56,10 @@ void upload_field_constants();
 cudaError_t configure_witness_kernel();   // once per device, before the first launch_witness on it
 void launch_witness(const DevProgram& P, uint8_t* w_all, size_t stride_elems, const uint8_t* inputs, uint32_t batch, cudaStream_t st);
 
+// circom's `===` check for a batch of witnesses in one launch, nothing stored: first_bad[e] (initialised to 0xffffffff by the
+// caller) = smallest row of email e with <A,w><B,w> != <C,w>
+void launch_check_rows(const DevR1cs& R, const uint8_t* w_all, size_t stride_elems, uint32_t batch, uint32_t* first_bad, cudaStream_t st);
+
 // a[i] = <A_i, w>, b[i] = <B_i, w> in Montgomery form for i < n_constraints, the n_public + 1 extra rows of the
 // Groth16 QAP (a = w_j, b = 0), zero padding up to n; also checks <A,w><B,w> = <C,w> and atomically records the
 // smallest violated row in *first_bad (initialised to 0xffffffff by the caller).

@@ -1042,16 +1042,8 @@ static void do_witness(zke_ctx* x, zke_ctx::Slot& S, const uint8_t* inputs, size
 
 // constraint check only (no zkey needed): uses scratch a/b vectors sized to n_constraints
 static int do_check(zke_ctx* x, zke_ctx::Slot& S, size_t batch, int32_t* status, std::string& msg) {
-    const Circuit& c = x->circuit->c;
-    const uint32_t rows = c.n_constraints + c.n_public() + 1;
-    DevBuf ta, tb;
-    uint8_t *pa, *pb;
-    if (x->lanes[0].va.p && x->lanes[0].va.bytes >= (size_t)rows * 32) { pa = x->lanes[0].va.p; pb = x->lanes[0].vb.p; }
-    else { ta.alloc((size_t)rows * 32); tb.alloc((size_t)rows * 32); pa = ta.p; pb = tb.p; }
     CUDA_OK(cudaMemsetAsync(S.first_bad.p, 0xff, 4 * batch, x->stream));
-    for (size_t e = 0; e < batch; ++e) {
-        dev::launch_build_ab(x->r1cs, S.w_all.p + 32 * x->stride * e, pa, pb, nullptr, rows, (uint32_t*)S.first_bad.p + e, x->stream);
-    }
+    dev::launch_check_rows(x->r1cs, S.w_all.p, x->stride, (uint32_t)batch, (uint32_t*)S.first_bad.p, x->stream);   // one launch, no a / b vectors
     CHECK_LAUNCH();
     CUDA_OK(cudaMemcpyAsync(x->bad_host.data(), S.first_bad.p, 4 * batch, cudaMemcpyDeviceToHost, x->stream));
     CUDA_OK(cudaStreamSynchronize(x->stream));
